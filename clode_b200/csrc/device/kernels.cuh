@@ -1,0 +1,324 @@
+// kernels.cuh — the four ensemble kernels (sm_100a), one ODE instance per thread.
+//
+//   clode_transient          <- clode/cpp/transient.cl:9-77
+//   clode_initialize_observer<- clode/cpp/initializeObserver.cl:9-83
+//   clode_features           <- clode/cpp/features.cl:10-106
+//   clode_trajectory         <- clode/cpp/trajectory.cl:14-112
+//
+// Data layout (identical to the reference API): every ensemble array is
+// variable-major with row pitch n = number of instances in the launch, so lane i of a
+// warp touches element [row*n + i] and each warp-wide access is one contiguous,
+// fully-coalesced 128/256-byte segment.  State, RK stages, parameters, aux and observer
+// data of an instance live in registers for the whole time loop; HBM is touched only in
+// the prologue / epilogue (and by trajectory stores).
+//
+// Time loop: an ATTEMPT loop (see steppers.cuh).  A lane leaves it when its instance is
+// finished; with CLODE_WORK_QUEUE the lane then pulls the next unprocessed instance from
+// a global counter instead of idling (persistent threads, warp-aggregated atomics).
+#ifndef CLODE_KERNELS_CUH
+#define CLODE_KERNELS_CUH
+
+#ifndef CLODE_BLOCK
+#define CLODE_BLOCK 64
+#endif
+#ifndef CLODE_MIN_BLOCKS
+#define CLODE_MIN_BLOCKS 1
+#endif
+
+// Launch arguments, one struct by value (lands in the constant bank; uniform loads).
+// Scalars travel as double and are narrowed on the device when realtype is float — the
+// same round-to-nearest conversion the reference does on the host (CLODE.cpp:292-300, 377-394).
+struct KernelArgs {
+    double t0, t1;
+    double sp_dt, sp_dtmax, sp_abstol, sp_reltol;
+    unsigned int sp_max_steps, sp_max_store, sp_nout;
+    unsigned int op_max_event_count;
+    double op_min_x_amp, op_min_imi, op_nhood_radius, op_x_up, op_x_down, op_dx_up, op_dx_down, op_eps_dx;
+    unsigned long long n;          // instances in this launch == row pitch of every array
+    const void *x0, *pars;         // [N_VAR][n], [N_PAR][n]
+    void *xf;                      // [N_VAR][n]
+    unsigned long long *rng;       // [2][n]
+    void *dt, *tf;                 // [n]
+    unsigned int *steps;           // [n] accepted steps of this call (may be null)
+    void *od_real;                 // observer state, [n_od_real][n]
+    unsigned int *od_uint;         // observer state, [n_od_uint][n]
+    void *F;                       // [n_features][n]
+    void *tr_t, *tr_x, *tr_dx, *tr_aux; // [rows][n], [rows][N_VAR][n], [rows][N_VAR][n], [rows][N_AUX][n]
+    int *n_stored;                 // [n]
+    unsigned long long *queue;     // work-queue head (CLODE_WORK_QUEUE)
+};
+
+CLODE_DEV SolverParams solver_params(const KernelArgs &a)
+{
+    SolverParams sp;
+    sp.dt = (realtype)a.sp_dt; sp.dtmax = (realtype)a.sp_dtmax;
+    sp.abstol = (realtype)a.sp_abstol; sp.reltol = (realtype)a.sp_reltol;
+    sp.max_steps = a.sp_max_steps; sp.max_store = a.sp_max_store; sp.nout = a.sp_nout;
+    return sp;
+}
+CLODE_DEV ObserverParams observer_params(const KernelArgs &a)
+{
+    ObserverParams op;
+    op.eVarIx = E_VAR_IX; op.fVarIx = F_VAR_IX;
+    op.maxEventCount = a.op_max_event_count; op.maxEventTimestamps = N_STORE_EVENTS;
+    op.minXamp = (realtype)a.op_min_x_amp; op.minIMI = (realtype)a.op_min_imi;
+    op.nHoodRadius = (realtype)a.op_nhood_radius;
+    op.xUpThresh = (realtype)a.op_x_up; op.xDownThresh = (realtype)a.op_x_down;
+    op.dxUpThresh = (realtype)a.op_dx_up; op.dxDownThresh = (realtype)a.op_dx_down;
+    op.eps_dx = (realtype)a.op_eps_dx;
+    return op;
+}
+
+// prologue shared by all kernels (transient.cl:28-52): coalesced loads, first noise draw, slope at t0
+CLODE_DEV void load_instance(Instance &I, const KernelArgs &a, const size_t i)
+{
+    const size_t n = a.n;
+    const realtype *x0 = (const realtype *)a.x0, *pars = (const realtype *)a.pars;
+    I.t = (realtype)a.t0;
+    I.dt = ((const realtype *)a.dt)[i];
+#pragma unroll
+    for (int j = 0; j < N_PAR; ++j)
+        I.p[j] = __ldg(pars + (size_t)j * n + i);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        I.x[j] = x0[(size_t)j * n + i];
+    I.rng.s0 = a.rng[i];
+    I.rng.s1 = a.rng[n + i];
+    I.rng.have_spare = false;
+    I.rng.spare = ZERO;
+#pragma unroll
+    for (int j = 0; j < NA_; ++j)
+        I.aux[j] = ZERO;
+#pragma unroll
+    for (int j = 0; j < NW_; ++j)
+        I.w[j] = ZERO;
+    draw_noise(I);
+    getRHS(I.t, I.x, I.p, I.k1, I.aux, I.w);
+}
+
+// epilogue (transient.cl:64-76)
+CLODE_DEV void store_instance(const Instance &I, const KernelArgs &a, const size_t i, const unsigned int steps)
+{
+    const size_t n = a.n;
+    realtype *xf = (realtype *)a.xf;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        xf[(size_t)j * n + i] = I.x[j];
+    a.rng[i] = I.rng.s0;
+    a.rng[n + i] = I.rng.s1;
+    ((realtype *)a.dt)[i] = I.dt;
+    ((realtype *)a.tf)[i] = I.t;
+    if (a.steps) a.steps[i] = steps;
+}
+
+// advance by one ATTEMPT; true when an accepted (or abandoned, flag -1) step completed
+CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const realtype t_end)
+{
+#if CLODE_ADAPTIVE
+    return adaptive_attempt(I, h, clean, sp, t_end);
+#else
+    step_fixed(I);
+    return true;
+#endif
+}
+
+// index of the instance this thread works on first, and how it gets the next one
+struct WorkSource {
+    size_t n;
+#ifdef CLODE_WORK_QUEUE
+    unsigned long long *head;
+    // warp-aggregated fetch: one atomic per warp per refill round
+    __device__ __forceinline__ size_t next()
+    {
+        const unsigned int active = __activemask();
+        const int leader = __ffs(active) - 1;
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(head, (unsigned long long)__popc(active));
+        base = __shfl_sync(active, base, leader);
+        return (size_t)(base + __popc(active & ((1u << lane) - 1u)));
+    }
+    __device__ __forceinline__ size_t first() { return next(); }
+#else
+    __device__ __forceinline__ size_t first() { return blockIdx.x * (size_t)blockDim.x + threadIdx.x; }
+    __device__ __forceinline__ size_t next() { return n; }
+#endif
+};
+
+CLODE_DEV WorkSource work_source(const KernelArgs &a)
+{
+    WorkSource w;
+    w.n = a.n;
+#ifdef CLODE_WORK_QUEUE
+    w.head = a.queue;
+#endif
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_transient(const __grid_constant__ KernelArgs a)
+{
+    const SolverParams sp = solver_params(a);
+    const realtype t_end = (realtype)a.t1;
+    WorkSource work = work_source(a);
+    for (size_t i = work.first(); i < a.n; i = work.next()) {
+        Instance I;
+        load_instance(I, a, i);
+        unsigned int step = 0;
+        realtype h = I.dt;
+        bool clean = true;
+        while (I.t <= t_end && step < sp.max_steps) {
+            if (advance(I, h, clean, sp, t_end))
+                ++step;
+        }
+        store_instance(I, a, i, step);
+    }
+}
+
+#ifdef CLODE_WITH_FEATURES
+// ------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_initialize_observer(const __grid_constant__ KernelArgs a)
+{
+    const SolverParams sp = solver_params(a);
+    const ObserverParams op = observer_params(a);
+    const realtype t_end = (realtype)a.t1;
+    WorkSource work = work_source(a);
+    for (size_t i = work.first(); i < a.n; i = work.next()) {
+        Instance I;
+        load_instance(I, a, i);
+        Observer ob;
+        ob.init(I);
+#if CLODE_TWO_PASS
+        {
+            unsigned int step = 0;
+            realtype h = I.dt;
+            bool clean = true;
+            while (I.t < t_end && step < sp.max_steps) { // strict '<' (initializeObserver.cl:62)
+                if (advance(I, h, clean, sp, t_end)) {
+                    ++step;
+                    ob.warmup(I, op);
+                }
+            }
+            // rewind; dt and the RNG state are NOT written back (initializeObserver.cl:72-82)
+            I.t = (realtype)a.t0;
+            const realtype *x0 = (const realtype *)a.x0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+                I.x[j] = x0[(size_t)j * a.n + i];
+            getRHS(I.t, I.x, I.p, I.k1, I.aux, I.w);
+        }
+#endif
+        ob.arm(I, op);
+        ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit(st);
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_features(const __grid_constant__ KernelArgs a)
+{
+    const SolverParams sp = solver_params(a);
+    const ObserverParams op = observer_params(a);
+    const realtype t_end = (realtype)a.t1;
+    WorkSource work = work_source(a);
+    for (size_t i = work.first(); i < a.n; i = work.next()) {
+        Instance I;
+        load_instance(I, a, i);
+        Observer ob;
+        {
+            ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+            ob.visit(ld);
+        }
+        unsigned int step = 0;
+        realtype h = I.dt;
+        bool clean = true;
+        bool live = I.t <= t_end && step < sp.max_steps;
+        while (live) {
+            if (advance(I, h, clean, sp, t_end)) {
+                ++step;
+                // features.cl:71-81: update, then event test, then event features
+                ob.update(I, op);
+                bool terminal = false;
+                if (ob.event(I, op))
+                    terminal = ob.on_event(I, op);
+                live = !terminal && I.t <= t_end && step < sp.max_steps;
+            }
+        }
+        FeatureOut out = {(realtype *)a.F, (size_t)a.n, i, 0};
+        ob.emit(out);
+        ob.rebase(I.t - (realtype)a.t0);
+        ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit(st);
+        store_instance(I, a, i, step);
+    }
+}
+
+// number of observer-state rows, for the host allocator
+extern "C" __global__ void clode_observer_layout(int *out)
+{
+    Observer ob;
+    ObsCount c = {0, 0};
+    ob.visit(c);
+    out[0] = c.nreal;
+    out[1] = c.nuint;
+    out[2] = CLODE_TWO_PASS;
+}
+#endif // CLODE_WITH_FEATURES
+
+#ifdef CLODE_WITH_TRAJECTORY
+// ------------------------------------------------------------------------------------------
+// Row r of the outputs holds stored point r of every instance:
+//   t[r*n + i], x[(r*N_VAR + j)*n + i], dx[...], aux[(r*N_AUX + j)*n + i].
+// A warp therefore writes one contiguous 32*sizeof(realtype) segment per variable per row.
+// The host allocates max_store+1 rows: row index max_store can be written.
+CLODE_DEV void store_point(const Instance &I, const KernelArgs &a, const size_t i, const size_t row)
+{
+    const size_t n = a.n;
+    ((realtype *)a.tr_t)[row * n + i] = I.t;
+    realtype *x = (realtype *)a.tr_x + row * n * NV + i;
+    realtype *dx = (realtype *)a.tr_dx + row * n * NV + i;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        __stcs(x + (size_t)j * n, I.x[j]);
+        __stcs(dx + (size_t)j * n, I.k1[j]);
+    }
+#if N_AUX > 0
+    realtype *aux = (realtype *)a.tr_aux + row * n * N_AUX + i;
+#pragma unroll
+    for (int j = 0; j < N_AUX; ++j)
+        __stcs(aux + (size_t)j * n, I.aux[j]);
+#endif
+}
+
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_trajectory(const __grid_constant__ KernelArgs a)
+{
+    const SolverParams sp = solver_params(a);
+    const realtype t_end = (realtype)a.t1;
+    WorkSource work = work_source(a);
+    for (size_t i = work.first(); i < a.n; i = work.next()) {
+        Instance I;
+        load_instance(I, a, i);
+        unsigned int row = 0;
+        store_point(I, a, i, 0);
+        unsigned int step = 0;
+        realtype h = I.dt;
+        bool clean = true;
+        while (I.t <= t_end && step < sp.max_steps && row < sp.max_store) {
+            if (advance(I, h, clean, sp, t_end)) {
+                ++step;
+                if (step % sp.nout == 0) {
+                    ++row;
+                    store_point(I, a, i, row);
+                }
+            }
+        }
+        a.n_stored[i] = (int)row;
+        store_instance(I, a, i, step);
+    }
+}
+#endif // CLODE_WITH_TRAJECTORY
+
+#endif // CLODE_KERNELS_CUH

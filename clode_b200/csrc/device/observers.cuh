@@ -1,0 +1,733 @@
+// observers.cuh — on-the-fly feature observers fused into the step loop.
+//
+// Semantics follow clode/cpp/observers/observer_*.clh function by function (init /
+// warm-up / per-step update / event test / event features / feature read-out / time
+// re-base for continuation); the data layout does not:
+//   * every observer keeps ONLY the fields that can influence a feature (e.g. the
+//     3-deep x/dx history is kept for the feature/event variable alone, where the
+//     reference shifts 6*N_VAR values per step and reads 5 of them), so the state
+//     lives in registers;
+//   * the feature and event variable indices are compile-time constants
+//     (F_VAR_IX / E_VAR_IX), so `x[fVarIx]` never forces a register array into
+//     local memory;
+//   * between kernels the state is spilled to a structure-of-arrays record
+//     (field-major, one coalesced row per field) instead of the reference's
+//     array-of-structs `ObserverData` (clode/cpp/features.cl:45,91).
+//
+// Observer selection by macro, as in the reference (`oi.define`):
+//   USE_OBSERVER_BASIC, USE_OBSERVER_BASIC_ALLVAR, USE_OBSERVER_LOCAL_MAX,
+//   USE_OBSERVER_NEIGHBORHOOD_1, USE_OBSERVER_NEIGHBORHOOD_2, USE_OBSERVER_THRESHOLD_2
+#ifndef CLODE_OBSERVERS_CUH
+#define CLODE_OBSERVERS_CUH
+
+#ifndef N_STORE_EVENTS
+#define N_STORE_EVENTS 0
+#endif
+#define NS_ (N_STORE_EVENTS > 0 ? N_STORE_EVENTS : 1)
+
+// struct ObserverParams — clode/cpp/observers.cl:25-46 (kernel argument, by value).
+// eVarIx / fVarIx are carried for completeness; the kernels use E_VAR_IX / F_VAR_IX.
+struct ObserverParams {
+    unsigned int eVarIx, fVarIx, maxEventCount, maxEventTimestamps;
+    realtype minXamp, minIMI, nHoodRadius, xUpThresh, xDownThresh, dxUpThresh, dxDownThresh, eps_dx;
+};
+
+// ---- small building blocks -----------------------------------------------------------
+
+// (max, min, running mean) accumulator used for every per-event statistic
+struct Tri {
+    realtype hi, lo, mean;
+    __device__ __forceinline__ void reset() { hi = -BIG_REAL; lo = BIG_REAL; mean = ZERO; }
+    __device__ __forceinline__ void push(realtype v, unsigned int count)
+    {
+        hi = fmax(v, hi);
+        lo = fmin(v, lo);
+        runningMean(&mean, v, count);
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v) { v(hi); v(lo); v(mean); }
+};
+
+// first-occurrence arg-extrema over a 3-sample window (clODE_utilities.cl:49-128)
+CLODE_DEV int argmax3(realtype a, realtype b, realtype c, realtype &best)
+{
+    best = -BIG_REAL; int at = 0;
+    if (a > best) { best = a; at = 0; }
+    if (b > best) { best = b; at = 1; }
+    if (c > best) { best = c; at = 2; }
+    return at;
+}
+CLODE_DEV int argmin3(realtype a, realtype b, realtype c, realtype &best)
+{
+    best = BIG_REAL; int at = 0;
+    if (a < best) { best = a; at = 0; }
+    if (b < best) { best = b; at = 1; }
+    if (c < best) { best = c; at = 2; }
+    return at;
+}
+CLODE_DEV realtype pick3(const realtype v[3], int at) { return at == 0 ? v[0] : (at == 1 ? v[1] : v[2]); }
+
+// extents and means of all variables, slopes and aux variables
+struct Extents {
+    realtype xmax[NV], xmin[NV], xmean[NV], dxmax[NV], dxmin[NV];
+    realtype amax[NA_], amin[NA_], amean[NA_];
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xmax[j] = -BIG_REAL; xmin[j] = BIG_REAL; xmean[j] = ZERO;
+            dxmax[j] = -BIG_REAL; dxmin[j] = BIG_REAL;
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { amax[j] = -BIG_REAL; amin[j] = BIG_REAL; amean[j] = ZERO; }
+    }
+    // time-weighted means (all observers except nhood1)
+    __device__ __forceinline__ void update_time(const Instance &I, realtype dt, realtype span)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xmax[j] = fmax(I.x[j], xmax[j]);
+            xmin[j] = fmin(I.x[j], xmin[j]);
+            xmean[j] = runningMeanTime(xmean[j], I.x[j], dt, span);
+            dxmax[j] = fmax(I.k1[j], dxmax[j]);
+            dxmin[j] = fmin(I.k1[j], dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) {
+            amax[j] = fmax(I.aux[j], amax[j]);
+            amin[j] = fmin(I.aux[j], amin[j]);
+            amean[j] = runningMeanTime(amean[j], I.aux[j], dt, span);
+        }
+    }
+    // per-step means (nhood1: observer_neighborhood_1.clh:250-261)
+    __device__ __forceinline__ void update_count(const Instance &I, unsigned int count)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            xmax[j] = fmax(I.x[j], xmax[j]);
+            xmin[j] = fmin(I.x[j], xmin[j]);
+            runningMean(&xmean[j], I.x[j], count);
+            dxmax[j] = fmax(I.k1[j], dxmax[j]);
+            dxmin[j] = fmin(I.k1[j], dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) {
+            amax[j] = fmax(I.aux[j], amax[j]);
+            amin[j] = fmin(I.aux[j], amin[j]);
+            runningMean(&amean[j], I.aux[j], count);
+        }
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { v(xmax[j]); v(xmin[j]); v(xmean[j]); v(dxmax[j]); v(dxmin[j]); }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { v(amax[j]); v(amin[j]); v(amean[j]); }
+    }
+};
+
+// feature writer: F is feature-major, F[k * n + i]
+struct FeatureOut {
+    realtype *F;
+    size_t n;
+    size_t i;
+    int k;
+    __device__ __forceinline__ void put(realtype v) { F[(size_t)(k++) * n + i] = v; }
+};
+
+// write list[idx] = v without dynamic register indexing
+CLODE_DEV void list_set(realtype list[NS_], unsigned int idx, realtype v)
+{
+#pragma unroll
+    for (int j = 0; j < N_STORE_EVENTS; ++j)
+        if ((unsigned int)j == idx) list[j] = v;
+}
+
+// =======================================================================================
+#if defined(USE_OBSERVER_BASIC)
+// observer_basic.clh:21-90 — extent and mean of one variable, no events.
+#define CLODE_TWO_PASS 0
+struct Observer {
+    realtype xmax, xmin, xmean, dxmax, dxmin, t_last, t_start;
+    unsigned int steps;
+
+    __device__ __forceinline__ void init(const Instance &I)
+    {
+        xmax = -BIG_REAL; xmin = BIG_REAL; xmean = ZERO; dxmax = -BIG_REAL; dxmin = BIG_REAL;
+        t_last = I.t; t_start = I.t; steps = 0;
+    }
+    __device__ __forceinline__ void warmup(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void arm(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        const realtype dt = I.t - t_last;
+        t_last = I.t;
+        const realtype span = I.t - t_start;
+        xmax = fmax(I.x[F_VAR_IX], xmax);
+        xmin = fmin(I.x[F_VAR_IX], xmin);
+        xmean = runningMeanTime(xmean, I.x[F_VAR_IX], dt, span);
+        dxmax = fmax(I.k1[F_VAR_IX], dxmax);
+        dxmin = fmin(I.k1[F_VAR_IX], dxmin);
+    }
+    __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
+    __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+        o.put(xmax); o.put(xmin); o.put(xmean); o.put(dxmax); o.put(dxmin); o.put((realtype)steps);
+    }
+    __device__ __forceinline__ void rebase(realtype T) { t_start -= T; }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+        v(xmax); v(xmin); v(xmean); v(dxmax); v(dxmin); v(t_last); v(t_start); v(steps);
+    }
+};
+
+// =======================================================================================
+#elif defined(USE_OBSERVER_BASIC_ALLVAR)
+// observer_basic_allVar.clh:35-132 — extents and means of all variables and aux, no events.
+#define CLODE_TWO_PASS 0
+struct Observer {
+    Extents ext;
+    realtype t_last, t_start;
+    unsigned int steps;
+
+    __device__ __forceinline__ void init(const Instance &I) { ext.reset(); t_last = I.t; t_start = I.t; steps = 0; }
+    __device__ __forceinline__ void warmup(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void arm(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        const realtype dt = I.t - t_last;
+        t_last = I.t;
+        ext.update_time(I, dt, I.t - t_start);
+    }
+    __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
+    __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            o.put(ext.xmax[j]); o.put(ext.xmin[j]); o.put(ext.xmean[j]); o.put(ext.dxmax[j]); o.put(ext.dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { o.put(ext.amax[j]); o.put(ext.amin[j]); o.put(ext.amean[j]); }
+        o.put((realtype)steps);
+    }
+    __device__ __forceinline__ void rebase(realtype T) { t_start -= T; }
+    template <class V> __device__ __forceinline__ void visit(V &v) { ext.visit(v); v(t_last); v(t_start); v(steps); }
+};
+
+// =======================================================================================
+#elif defined(USE_OBSERVER_LOCAL_MAX)
+// observer_local_maximum.clh:54-328 — event = local maximum of x[fVar] (slope + -> -).
+#define CLODE_TWO_PASS 0
+struct Observer {
+    realtype tb[3], xf[3]; // time / feature-variable history (oldest first)
+    realtype d1, d2;       // feature-variable slope at the previous and the current step
+    Extents ext;
+    realtype t_peak[NS_], x_peak[NS_], t_dip[NS_], x_dip[NS_];
+    Tri imi, amp;
+    realtype t_start, t_last_max, t_last_min, x_last_min;
+    unsigned int events, steps;
+
+    __device__ __forceinline__ void init(const Instance &I)
+    {
+        tb[0] = tb[1] = ZERO; tb[2] = I.t;
+        xf[0] = xf[1] = ZERO; xf[2] = I.x[F_VAR_IX];
+        d1 = ZERO; d2 = I.k1[F_VAR_IX];
+        ext.reset();
+#pragma unroll
+        for (int j = 0; j < NS_; ++j) { t_peak[j] = x_peak[j] = t_dip[j] = x_dip[j] = ZERO; }
+        imi.reset(); amp.reset();
+        t_start = I.t; t_last_max = ZERO; t_last_min = ZERO; x_last_min = BIG_REAL;
+        events = 0; steps = 0;
+    }
+    __device__ __forceinline__ void warmup(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void arm(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        tb[0] = tb[1]; tb[1] = tb[2]; tb[2] = I.t;
+        xf[0] = xf[1]; xf[1] = xf[2]; xf[2] = I.x[F_VAR_IX];
+        d1 = d2; d2 = I.k1[F_VAR_IX];
+        ext.update_time(I, tb[2] - tb[1], I.t - t_start);
+        if (steps < 2) return;
+        if (d1 < 0.0 && d2 > 0.0) { // local minimum between maxima (:269-282)
+            realtype lowest;
+            const int at = argmin3(xf[0], xf[1], xf[2], lowest);
+            t_last_min = pick3(tb, at);
+            x_last_min = pick3(xf, at); // the value AT the arg-min (:276), not the running best
+            // the reference indexes [eventcount-1] without checking eventcount > 0
+            // (out-of-bounds write); guarded here and in the oracle
+            if (events > 0 && events <= N_STORE_EVENTS) {
+                list_set(t_dip, events - 1, t_last_min);
+                list_set(x_dip, events - 1, x_last_min);
+            }
+        }
+    }
+    __device__ __forceinline__ bool event(const Instance &, const ObserverParams &)
+    {
+        return steps >= 2 && d1 > 0.0 && d2 < 0.0;
+    }
+    __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &op)
+    {
+        realtype x_pk;
+        const int at = argmax3(xf[0], xf[1], xf[2], x_pk);
+        const realtype t_pk = pick3(tb, at);
+        x_pk = pick3(xf, at); // value AT the arg-max (differs from the running best only for NaN input)
+        ++events;
+        if (events > 1) {
+            imi.push(t_pk - t_last_max, events - 1);
+            amp.push(x_pk - x_last_min, events - 1);
+        }
+        t_last_max = t_pk;
+        if (events <= N_STORE_EVENTS) {
+            list_set(t_peak, events - 1, t_pk);
+            list_set(x_peak, events - 1, x_pk);
+        }
+        return events == op.maxEventCount;
+    }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+        const bool multi = events > 1;
+        o.put(multi ? imi.hi : ZERO); o.put(multi ? imi.lo : ZERO); o.put(multi ? imi.mean : ZERO);
+        o.put(multi ? amp.hi : ZERO); o.put(multi ? amp.lo : ZERO); o.put(multi ? amp.mean : ZERO);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            o.put(ext.xmax[j]); o.put(ext.xmin[j]); o.put(ext.xmean[j]); o.put(ext.dxmax[j]); o.put(ext.dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { o.put(ext.amax[j]); o.put(ext.amin[j]); o.put(ext.amean[j]); }
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) { o.put(t_peak[j]); o.put(x_peak[j]); o.put(t_dip[j]); o.put(x_dip[j]); }
+        o.put((realtype)events);
+        o.put((realtype)steps);
+    }
+    __device__ __forceinline__ void rebase(realtype T)
+    {
+        t_start -= T;
+        t_last_max = t_last_max - T;
+        t_last_min = t_last_min - T;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tb[k] = tb[k] - T;
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v(tb[k]); v(xf[k]); }
+        v(d1); v(d2);
+        ext.visit(v);
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) { v(t_peak[j]); v(x_peak[j]); v(t_dip[j]); v(x_dip[j]); }
+        imi.visit(v); amp.visit(v);
+        v(t_start); v(t_last_max); v(t_last_min); v(x_last_min);
+        v(events); v(steps);
+    }
+};
+
+// =======================================================================================
+#elif defined(USE_OBSERVER_NEIGHBORHOOD_1)
+// observer_neighborhood_1.clh:44-361 — centre = state at the first local minimum of
+// x[eVar]; event = ENTRY into the L2 ball around it (range-normalised coordinates).
+#define CLODE_TWO_PASS 0
+struct Observer {
+    realtype tb[3], xb[NV][3]; // the centre is captured from the history, so all variables are kept
+    realtype de1, de2, df1, df2; // slopes of the event / feature variable (previous, current)
+    realtype center[NV];
+    Extents ext;
+    Tri peaks_stat, period, step_dt;
+    realtype t_start, t_last_event;
+    unsigned int peaks, events, steps, found, inside;
+
+    __device__ __forceinline__ void init(const Instance &I)
+    {
+        tb[0] = tb[1] = ZERO; tb[2] = I.t;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { xb[j][0] = xb[j][1] = ZERO; xb[j][2] = I.x[j]; center[j] = ZERO; }
+        de1 = df1 = ZERO; de2 = I.k1[E_VAR_IX]; df2 = I.k1[F_VAR_IX];
+        ext.reset();
+        peaks_stat.reset(); period.reset(); step_dt.reset();
+        t_start = I.t; t_last_event = ZERO; // left unset by the reference (:93-157); never read before being written
+        peaks = events = steps = found = inside = 0;
+    }
+    __device__ __forceinline__ void warmup(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void arm(const Instance &, const ObserverParams &) {}
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        tb[0] = tb[1]; tb[1] = tb[2]; tb[2] = I.t;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { xb[j][0] = xb[j][1]; xb[j][1] = xb[j][2]; xb[j][2] = I.x[j]; }
+        de1 = de2; de2 = I.k1[E_VAR_IX];
+        df1 = df2; df2 = I.k1[F_VAR_IX];
+        step_dt.push(tb[2] - tb[1], steps);
+        ext.update_count(I, steps);
+        if (steps > 1) {
+            if (!found) {
+                if (de1 <= 0.0 && de2 > 0.0) {
+                    realtype lowest;
+                    const int at = argmin3(xb[E_VAR_IX][0], xb[E_VAR_IX][1], xb[E_VAR_IX][2], lowest);
+                    t_last_event = pick3(tb, at);
+                    found = 1;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) center[j] = pick3(xb[j], at);
+                }
+            } else if (df1 >= 0.0 && df2 < 0.0) {
+                peaks++;
+            }
+        }
+    }
+    __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
+    {
+        if (steps < 2 || !found) return false;
+        if (ext.xmax[F_VAR_IX] - ext.xmin[F_VAR_IX] < op.minXamp) return false;
+        const unsigned int was = inside;
+        realtype d[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) d[j] = fabs(I.x[j] - center[j]) / (ext.xmax[j] - ext.xmin[j]);
+        inside = norm_2(d, NV) <= op.nHoodRadius;
+        return inside & !was;
+    }
+    __device__ __forceinline__ bool on_event(const Instance &I, const ObserverParams &op)
+    {
+        ++events;
+        if (events > 1) {
+            peaks_stat.push((realtype)peaks, events - 1);
+            period.push(I.t - t_last_event, events - 1);
+        }
+        t_last_event = I.t;
+        peaks = 0;
+        return events >= op.maxEventCount;
+    }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+        const bool multi = events > 1;
+        o.put(multi ? period.hi : ZERO); o.put(multi ? period.lo : ZERO); o.put(multi ? period.mean : ZERO);
+        o.put(multi ? peaks_stat.hi : ZERO); o.put(multi ? peaks_stat.lo : ZERO); o.put(multi ? peaks_stat.mean : ZERO);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            o.put(ext.xmax[j]); o.put(ext.xmin[j]); o.put(ext.xmean[j]); o.put(ext.dxmax[j]); o.put(ext.dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { o.put(ext.amax[j]); o.put(ext.amin[j]); o.put(ext.amean[j]); }
+        o.put((realtype)(events - 1u)); // "period count": unsigned wrap when no event, as the reference (:343)
+        o.put((realtype)steps);
+        o.put(step_dt.hi); o.put(step_dt.lo); o.put(step_dt.mean);
+    }
+    __device__ __forceinline__ void rebase(realtype T)
+    {
+        t_start -= T;
+        t_last_event -= T;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tb[k] -= T;
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v(tb[k]);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { v(xb[j][0]); v(xb[j][1]); v(xb[j][2]); v(center[j]); }
+        v(de1); v(de2); v(df1); v(df2);
+        ext.visit(v);
+        peaks_stat.visit(v); period.visit(v); step_dt.visit(v);
+        v(t_start); v(t_last_event);
+        v(peaks); v(events); v(steps); v(found); v(inside);
+    }
+};
+
+// =======================================================================================
+#elif defined(USE_OBSERVER_NEIGHBORHOOD_2)
+// observer_neighborhood_2.clh:50-313 — two-pass: warm-up finds per-variable ranges; centre =
+// state when x[eVar] first drops through min + xDownThresh*range; event = EXIT from the ball.
+#define CLODE_TWO_PASS 1
+struct Observer {
+    realtype tb[3];
+    realtype xe1, xe2; // event-variable history (previous, current)
+    realtype df1, df2; // feature-variable slope (previous, current)
+    realtype center[NV], range[NV];
+    Extents ext;
+    realtype t_exit[NS_];
+    Tri peaks_stat, period, step_dt;
+    realtype t_start, t_last_event, x_threshold;
+    unsigned int peaks, found, inside, events, steps;
+
+    __device__ __forceinline__ void init(const Instance &I)
+    {
+        tb[0] = tb[1] = ZERO; tb[2] = I.t;
+        xe1 = ZERO; xe2 = I.x[E_VAR_IX];
+        df1 = ZERO; df2 = I.k1[F_VAR_IX];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { center[j] = I.x[j]; range[j] = ZERO; }
+        ext.reset();
+#pragma unroll
+        for (int j = 0; j < NS_; ++j) t_exit[j] = ZERO;
+        peaks_stat.reset(); period.reset(); step_dt.reset();
+        t_start = I.t; t_last_event = ZERO; x_threshold = ZERO;
+        peaks = found = inside = events = steps = 0;
+    }
+    __device__ __forceinline__ void warmup(const Instance &I, const ObserverParams &)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            ext.xmax[j] = fmax(I.x[j], ext.xmax[j]);
+            ext.xmin[j] = fmin(I.x[j], ext.xmin[j]);
+        }
+    }
+    __device__ __forceinline__ void arm(const Instance &, const ObserverParams &op)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) range[j] = ext.xmax[j] - ext.xmin[j];
+        x_threshold = ext.xmin[E_VAR_IX] + op.xDownThresh * range[E_VAR_IX];
+    }
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        tb[0] = tb[1]; tb[1] = tb[2]; tb[2] = I.t;
+        xe1 = xe2; xe2 = I.x[E_VAR_IX];
+        df1 = df2; df2 = I.k1[F_VAR_IX];
+        const realtype dt = tb[2] - tb[1];
+        step_dt.push(dt, steps);
+        ext.update_time(I, dt, I.t - t_start);
+        if (steps < 2) return;
+        if (found) {
+            if (df1 >= 0.0 && df2 < 0.0) peaks++;
+            return;
+        }
+        if (xe1 > x_threshold && xe2 < x_threshold) {
+            found = 1;
+            inside = 1;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) center[j] = I.x[j];
+        }
+    }
+    __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
+    {
+        if (steps < 2 || !found) return false;
+        realtype d[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) d[j] = (I.x[j] - center[j]) / range[j];
+        const unsigned int was = inside;
+        inside = norm_2(d, NV) < op.nHoodRadius;
+        return was && !inside;
+    }
+    __device__ __forceinline__ bool on_event(const Instance &I, const ObserverParams &op)
+    {
+        ++events;
+        if (events > 1) {
+            peaks_stat.push((realtype)peaks, events - 1);
+            period.push(I.t - t_last_event, events - 1);
+        }
+        t_last_event = I.t;
+        peaks = 0;
+        if (events <= N_STORE_EVENTS) list_set(t_exit, events - 1, I.t);
+        return events == op.maxEventCount;
+    }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+        const bool multi = events > 1;
+        o.put(multi ? period.hi : ZERO); o.put(multi ? period.lo : ZERO); o.put(multi ? period.mean : ZERO);
+        o.put(multi ? peaks_stat.hi : ZERO); o.put(multi ? peaks_stat.lo : ZERO); o.put(multi ? peaks_stat.mean : ZERO);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            o.put(ext.xmax[j]); o.put(ext.xmin[j]); o.put(ext.xmean[j]); o.put(range[j]); o.put(center[j]);
+            o.put(ext.dxmax[j]); o.put(ext.dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { o.put(ext.amax[j]); o.put(ext.amin[j]); o.put(ext.amean[j]); }
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) o.put(t_exit[j]);
+        o.put((realtype)events);
+        o.put((realtype)steps);
+        o.put(step_dt.hi); o.put(step_dt.lo); o.put(step_dt.mean);
+    }
+    __device__ __forceinline__ void rebase(realtype T)
+    {
+        t_start -= T;
+        t_last_event -= T;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tb[k] -= T;
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v(tb[k]);
+        v(xe1); v(xe2); v(df1); v(df2);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { v(center[j]); v(range[j]); }
+        ext.visit(v);
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) v(t_exit[j]);
+        peaks_stat.visit(v); period.visit(v); step_dt.visit(v);
+        v(t_start); v(t_last_event); v(x_threshold);
+        v(peaks); v(found); v(inside); v(events); v(steps);
+    }
+};
+
+// =======================================================================================
+#elif defined(USE_OBSERVER_THRESHOLD_2)
+// observer_threshold_2.clh:63-470 — two-pass Schmitt trigger on x[eVar]: warm-up finds the
+// global extent of x and dx, thresholds are fractions of it; event = upward crossing.
+#define CLODE_TWO_PASS 1
+struct Observer {
+    realtype tb[3], xf[3]; // time / feature-variable history
+    realtype d1, d2;       // feature-variable slope (previous, current)
+    Extents ext;
+    realtype t_up[NS_], t_down[NS_];
+    Tri peaks_stat, period, up_time, down_time, duty, dip, step_dt;
+    realtype down_mean;
+    realtype g_xmax, g_xmin, g_dxmax, g_dxmin, x_up, x_down, dx_up, dx_down;
+    realtype t_start, t_last_event, t_this_down, x_last_min;
+    unsigned int peaks, steps, events, up;
+
+    __device__ __forceinline__ void init(const Instance &I)
+    {
+        tb[0] = tb[1] = ZERO; tb[2] = I.t;
+        xf[0] = xf[1] = ZERO; xf[2] = I.x[F_VAR_IX];
+        d1 = ZERO; d2 = I.k1[F_VAR_IX];
+        ext.reset();
+#pragma unroll
+        for (int j = 0; j < NS_; ++j) { t_up[j] = ZERO; t_down[j] = ZERO; }
+        peaks_stat.reset(); period.reset(); up_time.reset(); down_time.reset(); duty.reset(); dip.reset();
+        step_dt.reset();
+        down_mean = ZERO;
+        g_xmax = -BIG_REAL; g_xmin = BIG_REAL; g_dxmax = -BIG_REAL; g_dxmin = BIG_REAL;
+        x_up = x_down = dx_up = dx_down = ZERO;
+        t_start = I.t; t_last_event = ZERO; t_this_down = ZERO; x_last_min = BIG_REAL;
+        peaks = steps = events = up = 0;
+    }
+    __device__ __forceinline__ void warmup(const Instance &I, const ObserverParams &)
+    {
+        g_xmax = fmax(g_xmax, I.x[E_VAR_IX]);
+        g_xmin = fmin(g_xmin, I.x[E_VAR_IX]);
+        g_dxmax = fmax(g_dxmax, I.k1[E_VAR_IX]);
+        g_dxmin = fmin(g_dxmin, I.k1[E_VAR_IX]);
+    }
+    __device__ __forceinline__ void arm(const Instance &I, const ObserverParams &op)
+    {
+        const realtype amp = g_xmax - g_xmin;
+        x_up = g_xmin + op.xUpThresh * amp;
+        x_down = op.xDownThresh > ZERO ? g_xmin + op.xDownThresh * amp : x_up;
+        dx_up = op.dxUpThresh * g_dxmax;
+        dx_down = op.dxDownThresh > ZERO ? op.dxDownThresh * g_dxmin : g_dxmin;
+        up = I.x[E_VAR_IX] > x_up ? 1 : 0;
+    }
+    __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
+    {
+        ++steps;
+        tb[0] = tb[1]; tb[1] = tb[2]; tb[2] = I.t;
+        xf[0] = xf[1]; xf[1] = xf[2]; xf[2] = I.x[F_VAR_IX];
+        d1 = d2; d2 = I.k1[F_VAR_IX];
+        const realtype dt = tb[2] - tb[1];
+        step_dt.push(dt, steps);
+        ext.update_time(I, dt, I.t - t_start);
+        if (steps > 1) {
+            if (d1 > 0.0 && d2 < 0.0) peaks++; // local maximum of the feature variable
+            if (d1 < 0.0 && d2 > 0.0) {        // local minimum: remember its value
+                (void)argmin3(xf[0], xf[1], xf[2], x_last_min);
+            }
+            if (up) {
+                if (I.x[E_VAR_IX] <= x_down && I.k1[E_VAR_IX] >= dx_down) { // downward crossing
+                    t_this_down = I.t;
+                    up = 0;
+                    if (events > 0 && events <= N_STORE_EVENTS) list_set(t_down, events - 1, t_this_down);
+                    down_mean = I.x[F_VAR_IX];
+                }
+            } else {
+                const realtype since = I.t - t_this_down;
+                if (since > 0.0) down_mean = runningMeanTime(down_mean, I.x[F_VAR_IX], dt, since);
+            }
+        }
+    }
+    __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
+    {
+        if (steps < 2) return false;
+        if (g_xmax - g_xmin < op.minXamp) return false;
+        if (up) return false;
+        return I.x[E_VAR_IX] > x_up && I.k1[E_VAR_IX] > dx_up;
+    }
+    __device__ __forceinline__ bool on_event(const Instance &I, const ObserverParams &op)
+    {
+        ++events;
+        up = 1;
+        const realtype now = I.t;
+        if (events > 1) {
+            const unsigned int n = events - 1;
+            peaks_stat.push((realtype)peaks, n);
+            const realtype this_period = now - t_last_event;
+            period.push(this_period, n);
+            const realtype this_up = t_this_down - t_last_event;
+            up_time.push(this_up, n);
+            down_time.push(now - t_this_down, n);
+            duty.push(this_up / this_period, n);
+            dip.push(down_mean - x_last_min, n);
+        }
+        if (events <= N_STORE_EVENTS) list_set(t_up, events - 1, now);
+        t_last_event = now;
+        peaks = 0;
+        return events == op.maxEventCount;
+    }
+    __device__ __forceinline__ void emit(FeatureOut &o) const
+    {
+        const bool multi = events > 1;
+#define PUT3(T) o.put(multi ? T.hi : ZERO); o.put(multi ? T.lo : ZERO); o.put(multi ? T.mean : ZERO)
+        PUT3(period); PUT3(peaks_stat); PUT3(up_time); PUT3(down_time); PUT3(duty); PUT3(dip);
+#undef PUT3
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            o.put(ext.xmax[j]); o.put(ext.xmin[j]); o.put(ext.xmean[j]); o.put(ext.dxmax[j]); o.put(ext.dxmin[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) { o.put(ext.amax[j]); o.put(ext.amin[j]); o.put(ext.amean[j]); }
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) { o.put(t_up[j]); o.put(t_down[j]); }
+        o.put((realtype)events);
+        o.put((realtype)steps);
+        o.put(step_dt.hi); o.put(step_dt.lo); o.put(step_dt.mean);
+    }
+    __device__ __forceinline__ void rebase(realtype T)
+    {
+        t_start -= T;
+        t_last_event -= T;
+        t_this_down -= T;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tb[k] -= T;
+    }
+    template <class V> __device__ __forceinline__ void visit(V &v)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { v(tb[k]); v(xf[k]); }
+        v(d1); v(d2);
+        ext.visit(v);
+#pragma unroll
+        for (int j = 0; j < N_STORE_EVENTS; ++j) { v(t_up[j]); v(t_down[j]); }
+        peaks_stat.visit(v); period.visit(v); up_time.visit(v); down_time.visit(v); duty.visit(v); dip.visit(v);
+        step_dt.visit(v);
+        v(down_mean);
+        v(g_xmax); v(g_xmin); v(g_dxmax); v(g_dxmin); v(x_up); v(x_down); v(dx_up); v(dx_down);
+        v(t_start); v(t_last_event); v(t_this_down); v(x_last_min);
+        v(peaks); v(steps); v(events); v(up);
+    }
+};
+
+#else
+#error "no observer selected"
+#endif
+
+// ---- structure-of-arrays persistence of the observer state -----------------------------
+struct ObsCount {
+    int nreal, nuint;
+    __device__ __forceinline__ void operator()(realtype &) { ++nreal; }
+    __device__ __forceinline__ void operator()(unsigned int &) { ++nuint; }
+};
+struct ObsStore {
+    realtype *r; unsigned int *u; size_t n, i; int kr, ku;
+    __device__ __forceinline__ void operator()(realtype &x) { r[(size_t)(kr++) * n + i] = x; }
+    __device__ __forceinline__ void operator()(unsigned int &x) { u[(size_t)(ku++) * n + i] = x; }
+};
+struct ObsLoad {
+    const realtype *r; const unsigned int *u; size_t n, i; int kr, ku;
+    __device__ __forceinline__ void operator()(realtype &x) { x = r[(size_t)(kr++) * n + i]; }
+    __device__ __forceinline__ void operator()(unsigned int &x) { x = u[(size_t)(ku++) * n + i]; }
+};
+
+#endif // CLODE_OBSERVERS_CUH

@@ -1,0 +1,65 @@
+// rng.cuh — per-instance random stream, bit-compatible with the reference's
+// xoroshiro128+ / polar Box-Muller (clode/cpp/clODE_random.cl:28-114).
+//
+// The integer recurrence is exact by construction.  The floating-point part is
+// written with explicit round-to-nearest intrinsics so that FMA contraction (on in
+// the production build) can never change the accept/reject decision of the polar
+// method (`w >= 1`, clODE_random.cl:100-105) and desynchronise the stream from the
+// CPU oracle; only log() (libdevice vs glibc) can differ in the last bit of the
+// returned variate, never in the number of draws consumed.
+#ifndef CLODE_RNG_CUH
+#define CLODE_RNG_CUH
+
+struct RngStream {
+    unsigned long long s0, s1;
+    realtype spare;
+    bool have_spare;
+};
+
+CLODE_DEV unsigned long long rng_next(RngStream &g)
+{
+    const unsigned long long a = g.s0;
+    unsigned long long b = g.s1;
+    const unsigned long long out = a + b;
+    b ^= a;
+    g.s0 = ((a << 55) | (a >> 9)) ^ b ^ (b << 14);
+    g.s1 = (b << 36) | (b >> 28);
+    return out;
+}
+
+#if defined(CLODE_SINGLE_PRECISION)
+CLODE_DEV realtype rng_mul(realtype a, realtype b) { return __fmul_rn(a, b); }
+CLODE_DEV realtype rng_add(realtype a, realtype b) { return __fadd_rn(a, b); }
+CLODE_DEV realtype rng_from_u64(unsigned long long u) { return __ull2float_rn(u); }
+#else
+CLODE_DEV realtype rng_mul(realtype a, realtype b) { return __dmul_rn(a, b); }
+CLODE_DEV realtype rng_add(realtype a, realtype b) { return __dadd_rn(a, b); }
+CLODE_DEV realtype rng_from_u64(unsigned long long u) { return __ull2double_rn(u); }
+#endif
+
+// uniform on [0,1]: u64 -> real (rounded) times 2^-64  (clODE_random.cl:81-85)
+CLODE_DEV realtype rng_uniform(RngStream &g)
+{
+    return rng_mul(rng_from_u64(rng_next(g)), RCONST(5.421010862427522e-20));
+}
+
+// N(0,1) by the Marsaglia polar method; the second variate of each pair is kept
+CLODE_DEV realtype rng_normal(RngStream &g)
+{
+    if (g.have_spare) {
+        g.have_spare = false;
+        return g.spare;
+    }
+    realtype a, b, q;
+    do {
+        a = rng_add(rng_mul(RCONST(2.0), rng_uniform(g)), -ONE);
+        b = rng_add(rng_mul(RCONST(2.0), rng_uniform(g)), -ONE);
+        q = rng_add(rng_mul(a, a), rng_mul(b, b));
+    } while (q >= ONE);
+    q = sqrt(rng_mul(-RCONST(2.0), log(q)) / q);
+    g.spare = rng_mul(b, q);
+    g.have_spare = true;
+    return rng_mul(a, q);
+}
+
+#endif // CLODE_RNG_CUH

@@ -1,0 +1,947 @@
+// clode_rt.cpp — implementation of the C ABI in include/clode_rt.h.
+//
+// Replaces the reference's OpenCLResource (clode/cpp/OpenCLResource.cpp) and the
+// cl::Buffer / cl::Kernel plumbing inside CLODE.cpp / CLODEfeatures.cpp / CLODEtrajectory.cpp
+// with: CUDA driver API (primary context per device, one stream per simulation object),
+// NVRTC JIT of the engine + user RHS into an sm_100a cubin (with an on-disk cache), and
+// device buffers in the reference's variable-major layout.
+#include "clode_rt.h"
+
+#include "cuda_dl.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+using namespace clode;
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+
+// ---- embedded device sources (generated from clode_b200/csrc/device/*.cuh by build.py) ----
+struct EmbeddedSource {
+    const char *name;
+    const char *text;
+};
+#include "device_sources.inc" // defines: static const EmbeddedSource kDeviceSources[]; static const int kNumDeviceSources;
+
+const char *kStepperNames[] = {"euler", "heun", "rk4", "bs23", "dopri5", "seuler"};
+const char *kStepperDefines[] = {"EXPLICIT_EULER", "EXPLICIT_HEUN", "EXPLICIT_RK4",
+                                 "EXPLICIT_BS23", "EXPLICIT_DOPRI5", "STOCHASTIC_EULER"};
+const char *kObserverNames[] = {"basic", "basicall", "localmax", "nhood1", "nhood2", "thresh2"};
+const char *kObserverDefines[] = {"USE_OBSERVER_BASIC", "USE_OBSERVER_BASIC_ALLVAR", "USE_OBSERVER_LOCAL_MAX",
+                                  "USE_OBSERVER_NEIGHBORHOOD_1", "USE_OBSERVER_NEIGHBORHOOD_2",
+                                  "USE_OBSERVER_THRESHOLD_2"};
+
+int find_name(const char *const *names, int n, const char *s)
+{
+    if (!s) return -1;
+    for (int i = 0; i < n; ++i)
+        if (std::strcmp(names[i], s) == 0) return i;
+    return -1;
+}
+
+int observer_feature_count(int observer, int nv, int na, int ns)
+{
+    switch (observer) {
+    case 0: return 6;
+    case 1: return 5 * nv + 3 * na + 1;
+    case 2: return 6 + 5 * nv + 3 * na + 4 * ns + 2;
+    case 3: return 6 + 5 * nv + 3 * na + 5;
+    case 4: return 6 + 7 * nv + 3 * na + ns + 5;
+    case 5: return 18 + 5 * nv + 3 * na + 2 * ns + 5;
+    }
+    return 0;
+}
+
+struct ProgramSpec {
+    std::string rhs;
+    int stepper = 2, observer = 0;
+    bool single = false;
+    int n_var = 0, n_par = 0, n_aux = 0, n_wiener = 0;
+    int f_var = 0, e_var = 0, n_store = 0;
+    int kernels = CLODE_KERNEL_TRANSIENT;
+    bool bit_exact = false, work_queue = false;
+    int block = 64, min_blocks = 1;
+};
+
+int parse_desc(const clode_program_desc *d, ProgramSpec &s)
+{
+    if (!d || !d->rhs_source) return fail(CLODE_ERR_INVALID, "program description or rhs_source is null");
+    s.rhs = d->rhs_source;
+    s.stepper = find_name(kStepperNames, 6, d->stepper);
+    if (s.stepper < 0) return fail(CLODE_ERR_INVALID, std::string("unknown stepper: ") + (d->stepper ? d->stepper : "(null)"));
+    s.observer = d->observer ? find_name(kObserverNames, 6, d->observer) : 0;
+    if (s.observer < 0) return fail(CLODE_ERR_INVALID, std::string("unknown observer: ") + d->observer);
+    s.single = d->single_precision != 0;
+    s.n_var = d->n_var; s.n_par = d->n_par; s.n_aux = d->n_aux; s.n_wiener = d->n_wiener;
+    if (s.n_var < 1) return fail(CLODE_ERR_INVALID, "n_var must be >= 1");
+    if (s.n_par < 0 || s.n_aux < 0 || s.n_wiener < 0) return fail(CLODE_ERR_INVALID, "negative dimension");
+    s.f_var = d->f_var_ix; s.e_var = d->e_var_ix; s.n_store = d->n_store_events;
+    if (s.f_var < 0 || s.f_var >= s.n_var || s.e_var < 0 || s.e_var >= s.n_var)
+        return fail(CLODE_ERR_INVALID, "f_var_ix / e_var_ix out of range");
+    if (s.n_store < 0) return fail(CLODE_ERR_INVALID, "n_store_events must be >= 0");
+    s.kernels = d->kernels | CLODE_KERNEL_TRANSIENT;
+    s.bit_exact = d->bit_exact != 0;
+    if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
+    s.work_queue = d->work_queue != 0;
+    s.block = d->block_size > 0 ? d->block_size : 64;
+    if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
+    s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 1;
+    return CLODE_OK;
+}
+
+std::vector<std::string> compile_options(const ProgramSpec &s)
+{
+    std::vector<std::string> o;
+    o.push_back("--gpu-architecture=sm_100a");
+    o.push_back("--std=c++17");
+    o.push_back("-default-device");
+    o.push_back("-lineinfo");
+    o.push_back(s.bit_exact ? "--fmad=false" : "--fmad=true");
+    o.push_back(s.single ? "-DCLODE_SINGLE_PRECISION" : "-DCLODE_DOUBLE_PRECISION");
+    o.push_back(std::string("-D") + kStepperDefines[s.stepper]);
+    o.push_back(std::string("-D") + kObserverDefines[s.observer]);
+    o.push_back("-DN_VAR=" + std::to_string(s.n_var));
+    o.push_back("-DN_PAR=" + std::to_string(s.n_par));
+    o.push_back("-DN_AUX=" + std::to_string(s.n_aux));
+    o.push_back("-DN_WIENER=" + std::to_string(s.n_wiener));
+    o.push_back("-DN_STORE_EVENTS=" + std::to_string(s.n_store));
+    o.push_back("-DF_VAR_IX=" + std::to_string(s.f_var));
+    o.push_back("-DE_VAR_IX=" + std::to_string(s.e_var));
+    o.push_back("-DCLODE_BLOCK=" + std::to_string(s.block));
+    o.push_back("-DCLODE_MIN_BLOCKS=" + std::to_string(s.min_blocks));
+    if (s.kernels & CLODE_KERNEL_FEATURES) o.push_back("-DCLODE_WITH_FEATURES");
+    if (s.kernels & CLODE_KERNEL_TRAJECTORY) o.push_back("-DCLODE_WITH_TRAJECTORY");
+    if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
+    if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
+    return o;
+}
+
+// top-level translation unit: engine headers, then — as the reference does
+// (clode/cpp/CLODE.cpp:148) — the user's RHS source as the last text.
+const char *kMainSource =
+    "#include \"cl_compat.cuh\"\n"
+    "#include \"rng.cuh\"\n"
+    "#include \"steppers.cuh\"\n"
+    "#include \"observers.cuh\"\n"
+    "#include \"kernels.cuh\"\n"
+    "// OpenCL C address-space keywords without underscores, for the RHS text only\n"
+    "#define global\n"
+    "#define local\n"
+    "#define constant const\n"
+    "#include \"clode_user_rhs.cl\"\n";
+
+std::string full_source(const ProgramSpec &s)
+{
+    std::ostringstream os;
+    os << "// options:";
+    for (auto &o : compile_options(s)) os << ' ' << o;
+    os << "\n";
+    for (int i = 0; i < kNumDeviceSources; ++i)
+        os << "// ======== " << kDeviceSources[i].name << " ========\n" << kDeviceSources[i].text << "\n";
+    os << "// ======== user RHS ========\n" << s.rhs << "\n";
+    return os.str();
+}
+
+uint64_t fnv1a(const std::string &s, uint64_t h)
+{
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+std::string cache_dir()
+{
+    const char *env = std::getenv("CLODE_CACHE_DIR");
+    if (env && *env) return env;
+    Dl_info info;
+    if (dladdr((void *)&fnv1a, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        if (k != std::string::npos) return p.substr(0, k) + "/_cubin_cache";
+    }
+    return "/tmp/clode_cubin_cache";
+}
+
+int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &log)
+{
+    // cache lookup
+    std::string key_src = full_source(s);
+    uint64_t h1 = fnv1a(key_src, 1469598103934665603ull), h2 = fnv1a(key_src, 0x9e3779b97f4a7c15ull);
+    char name[64];
+    std::snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+    const bool use_cache = !(std::getenv("CLODE_NO_CACHE") && *std::getenv("CLODE_NO_CACHE") == '1');
+    std::string dir = cache_dir(), path = dir + "/" + name;
+    if (use_cache) {
+        std::ifstream f(path, std::ios::binary);
+        if (f) {
+            cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            if (!cubin.empty()) {
+                log = "(cubin cache hit: " + path + ")";
+                return CLODE_OK;
+            }
+        }
+    }
+    std::string why;
+    NvrtcApi *rtc = nvrtc(&why);
+    if (!rtc) return fail(CLODE_ERR_NO_DRIVER, why);
+
+    std::vector<const char *> hdr_text, hdr_name;
+    for (int i = 0; i < kNumDeviceSources; ++i) {
+        hdr_text.push_back(kDeviceSources[i].text);
+        hdr_name.push_back(kDeviceSources[i].name);
+    }
+    hdr_text.push_back(s.rhs.c_str());
+    hdr_name.push_back("clode_user_rhs.cl");
+
+    nvrtcProgram prog;
+    nvrtcResult r = rtc->nvrtcCreateProgram(&prog, kMainSource, "clode_program.cu", (int)hdr_text.size(),
+                                            hdr_text.data(), hdr_name.data());
+    if (r != NVRTC_SUCCESS) return fail(CLODE_ERR_BUILD, std::string("nvrtcCreateProgram: ") + rtc->nvrtcGetErrorString(r));
+    std::vector<std::string> opts = compile_options(s);
+    std::vector<const char *> copts;
+    for (auto &o : opts) copts.push_back(o.c_str());
+    r = rtc->nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    size_t log_size = 0;
+    rtc->nvrtcGetProgramLogSize(prog, &log_size);
+    log.assign(log_size > 0 ? log_size : 1, '\0');
+    if (log_size > 1) rtc->nvrtcGetProgramLog(prog, &log[0]);
+    while (!log.empty() && log.back() == '\0') log.pop_back();
+    if (r != NVRTC_SUCCESS) {
+        rtc->nvrtcDestroyProgram(&prog);
+        return fail(CLODE_ERR_BUILD, std::string("NVRTC compilation failed (") + rtc->nvrtcGetErrorString(r) + ")\n" + log);
+    }
+    size_t size = 0;
+    r = rtc->nvrtcGetCUBINSize(prog, &size);
+    if (r != NVRTC_SUCCESS || size == 0) {
+        rtc->nvrtcDestroyProgram(&prog);
+        return fail(CLODE_ERR_BUILD, "nvrtcGetCUBINSize failed");
+    }
+    cubin.resize(size);
+    rtc->nvrtcGetCUBIN(prog, cubin.data());
+    rtc->nvrtcDestroyProgram(&prog);
+    if (use_cache) {
+        mkdir(dir.c_str(), 0755);
+        std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+        std::ofstream f(tmp, std::ios::binary);
+        if (f) {
+            f.write(cubin.data(), (std::streamsize)cubin.size());
+            f.close();
+            std::rename(tmp.c_str(), path.c_str());
+        }
+    }
+    return CLODE_OK;
+}
+
+// ---- launch-argument block: must match struct KernelArgs in device/kernels.cuh ----
+struct KernelArgs {
+    double t0, t1;
+    double sp_dt, sp_dtmax, sp_abstol, sp_reltol;
+    unsigned int sp_max_steps, sp_max_store, sp_nout;
+    unsigned int op_max_event_count;
+    double op_min_x_amp, op_min_imi, op_nhood_radius, op_x_up, op_x_down, op_dx_up, op_dx_down, op_eps_dx;
+    unsigned long long n;
+    CUdeviceptr x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
+};
+
+std::string cu_error(DriverApi *d, CUresult r)
+{
+    const char *name = nullptr, *str = nullptr;
+    d->cuGetErrorName(r, &name);
+    d->cuGetErrorString(r, &str);
+    return std::string(name ? name : "CUDA_ERROR") + " (" + (str ? str : "?") + ")";
+}
+
+struct Buffer {
+    CUdeviceptr ptr = 0;
+    size_t bytes = 0;
+};
+
+} // namespace
+
+struct clode_sim {
+    DriverApi *d = nullptr;
+    int device = 0;
+    CUdevice dev = 0;
+    CUcontext ctx = nullptr;
+    CUstream stream = nullptr;
+    CUevent ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    size_t total_mem = 0;
+
+    ProgramSpec spec;
+    bool built = false;
+    std::string build_log;
+    CUmodule module = nullptr;
+    CUfunction k_transient = nullptr, k_init = nullptr, k_features = nullptr, k_trajectory = nullptr, k_layout = nullptr;
+    int od_nreal = 0, od_nuint = 0, two_pass = 0;
+    int n_features = 0;
+
+    size_t n = 0;
+    size_t real_size = 8;
+    Buffer x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
+    size_t tr_rows = 0; // allocated trajectory rows (max_store + 1)
+    bool observer_initialized = false;
+
+    double t0 = 0.0, t1 = 0.0;
+    clode_solver_params sp{0.1, 0.5, 1e-6, 1e-3, 1000000u, 1000000u, 1u};
+    clode_observer_params op{0, 0, 100, 0, 0.0, 0.0, 0.05, 0.2, 0.2, 0.0, 0.0, 0.0};
+
+    float last_ms = 0.f;
+    uint64_t launches = 0;
+
+    struct Scope { // make the context current for the duration of a call
+        clode_sim *s;
+        explicit Scope(clode_sim *s_) : s(s_) { s->d->cuCtxPushCurrent(s->ctx); }
+        ~Scope() { CUcontext c; s->d->cuCtxPopCurrent(&c); }
+    };
+
+    int cu(CUresult r, const char *what)
+    {
+        if (r == CUDA_SUCCESS) return CLODE_OK;
+        return fail(CLODE_ERR_CUDA, std::string(what) + ": " + cu_error(d, r));
+    }
+
+    int alloc(Buffer &b, size_t bytes, const char *what)
+    {
+        if (b.bytes == bytes && b.ptr) return CLODE_OK;
+        if (b.ptr) { d->cuMemFree(b.ptr); b.ptr = 0; b.bytes = 0; }
+        if (bytes == 0) return CLODE_OK;
+        if (bytes > total_mem) return fail(CLODE_ERR_MEMORY, std::string(what) + ": requested allocation exceeds device memory");
+        CUresult r = d->cuMemAlloc(&b.ptr, bytes);
+        if (r != CUDA_SUCCESS) { b.ptr = 0; return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? CLODE_ERR_MEMORY : CLODE_ERR_CUDA, std::string(what) + ": " + cu_error(d, r)); }
+        b.bytes = bytes;
+        return CLODE_OK;
+    }
+    void release(Buffer &b)
+    {
+        if (b.ptr) d->cuMemFree(b.ptr);
+        b.ptr = 0; b.bytes = 0;
+    }
+
+    // host double[] -> device realtype[]
+    int upload_real(Buffer &b, const double *src, size_t count, const char *what)
+    {
+        if (count * real_size != b.bytes) return fail(CLODE_ERR_INVALID, std::string(what) + ": size mismatch");
+        if (count == 0) return CLODE_OK;
+        if (real_size == 8) return cu(d->cuMemcpyHtoD(b.ptr, src, count * 8), what);
+        std::vector<float> tmp(count);
+        for (size_t k = 0; k < count; ++k) tmp[k] = (float)src[k];
+        return cu(d->cuMemcpyHtoD(b.ptr, tmp.data(), count * 4), what);
+    }
+    int download_real(const Buffer &b, double *dst, size_t count, const char *what)
+    {
+        if (count * real_size > b.bytes) return fail(CLODE_ERR_INVALID, std::string(what) + ": size mismatch");
+        if (count == 0) return CLODE_OK;
+        if (real_size == 8) return cu(d->cuMemcpyDtoH(dst, b.ptr, count * 8), what);
+        std::vector<float> tmp(count);
+        int rc = cu(d->cuMemcpyDtoH(tmp.data(), b.ptr, count * 4), what);
+        if (rc) return rc;
+        for (size_t k = 0; k < count; ++k) dst[k] = (double)tmp[k];
+        return CLODE_OK;
+    }
+
+    void free_ensemble()
+    {
+        Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue};
+        for (Buffer *b : all) release(*b);
+        n = 0; tr_rows = 0; observer_initialized = false;
+    }
+
+    KernelArgs args() const
+    {
+        KernelArgs a;
+        std::memset(&a, 0, sizeof a);
+        a.t0 = t0; a.t1 = t1;
+        a.sp_dt = sp.dt; a.sp_dtmax = sp.dtmax; a.sp_abstol = sp.abstol; a.sp_reltol = sp.reltol;
+        a.sp_max_steps = sp.max_steps; a.sp_max_store = sp.max_store; a.sp_nout = sp.nout;
+        a.op_max_event_count = op.max_event_count;
+        a.op_min_x_amp = op.min_x_amp; a.op_min_imi = op.min_imi; a.op_nhood_radius = op.nhood_radius;
+        a.op_x_up = op.x_up_thresh; a.op_x_down = op.x_down_thresh; a.op_dx_up = op.dx_up_thresh;
+        a.op_dx_down = op.dx_down_thresh; a.op_eps_dx = op.eps_dx;
+        a.n = n;
+        a.x0 = x0.ptr; a.pars = pars.ptr; a.xf = xf.ptr; a.rng = rng.ptr; a.dt = dt.ptr; a.tf = tf.ptr;
+        a.steps = steps.ptr; a.od_real = od_real.ptr; a.od_uint = od_uint.ptr; a.F = F.ptr;
+        a.tr_t = tr_t.ptr; a.tr_x = tr_x.ptr; a.tr_dx = tr_dx.ptr; a.tr_aux = tr_aux.ptr;
+        a.n_stored = n_stored.ptr; a.queue = queue.ptr;
+        return a;
+    }
+
+    int grid_for(CUfunction f, unsigned &grid)
+    {
+        if (spec.work_queue) {
+            int per_sm = 1;
+            CUresult r = d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, spec.block, 0);
+            if (r != CUDA_SUCCESS) return cu(r, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
+            size_t want = (n + spec.block - 1) / spec.block;
+            size_t persistent = (size_t)std::max(per_sm, 1) * sm_count;
+            grid = (unsigned)std::min(want, persistent);
+        } else {
+            grid = (unsigned)((n + spec.block - 1) / spec.block);
+        }
+        if (grid == 0) grid = 1;
+        return CLODE_OK;
+    }
+
+    // launch `f` over the ensemble; when `timed_first`, (re)start the event pair
+    int launch(CUfunction f, const char *what, bool first, bool last)
+    {
+        if (!f) return fail(CLODE_ERR_STATE, std::string(what) + ": kernel not built");
+        if (n == 0) return fail(CLODE_ERR_STATE, std::string(what) + ": no problem data set (nPts == 0)");
+        int rc;
+        if (spec.work_queue) {
+            if ((rc = cu(d->cuMemsetD8Async(queue.ptr, 0, 8, stream), "reset work queue"))) return rc;
+        }
+        KernelArgs a = args();
+        void *params[] = {&a};
+        unsigned grid = 1;
+        if ((rc = grid_for(f, grid))) return rc;
+        if (first && (rc = cu(d->cuEventRecord(ev0, stream), "cuEventRecord"))) return rc;
+        if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, 0, stream, params, nullptr), what))) return rc;
+        ++launches;
+        if (last) {
+            if ((rc = cu(d->cuEventRecord(ev1, stream), "cuEventRecord"))) return rc;
+            if ((rc = cu(d->cuStreamSynchronize(stream), what))) return rc;
+            d->cuEventElapsedTime(&last_ms, ev0, ev1);
+        }
+        return CLODE_OK;
+    }
+};
+
+// =============================================================================================
+extern "C" {
+
+const char *clode_last_error(void) { return g_error.c_str(); }
+const char *clode_version(void) { return "clode_b200 0.1 (sm_100a, NVRTC)"; }
+void clode_free(void *p) { std::free(p); }
+
+int clode_device_count(int *count)
+{
+    if (!count) return fail(CLODE_ERR_INVALID, "count is null");
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (!d) { *count = 0; return fail(CLODE_ERR_NO_DRIVER, why); }
+    CUresult r = d->cuDeviceGetCount(count);
+    if (r != CUDA_SUCCESS) return fail(CLODE_ERR_CUDA, "cuDeviceGetCount: " + cu_error(d, r));
+    return CLODE_OK;
+}
+
+int clode_device_get_info(int device, clode_device_info *info)
+{
+    if (!info) return fail(CLODE_ERR_INVALID, "info is null");
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (!d) return fail(CLODE_ERR_NO_DRIVER, why);
+    int count = 0;
+    d->cuDeviceGetCount(&count);
+    if (device < 0 || device >= count) return fail(CLODE_ERR_INVALID, "device index out of range");
+    CUdevice dev;
+    CUresult r = d->cuDeviceGet(&dev, device);
+    if (r != CUDA_SUCCESS) return fail(CLODE_ERR_CUDA, "cuDeviceGet: " + cu_error(d, r));
+    std::memset(info, 0, sizeof *info);
+    d->cuDeviceGetName(info->name, sizeof info->name, dev);
+    d->cuDeviceGetAttribute(&info->cc_major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, dev);
+    d->cuDeviceGetAttribute(&info->cc_minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, dev);
+    d->cuDeviceGetAttribute(&info->multiprocessors, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+    int khz = 0;
+    d->cuDeviceGetAttribute(&khz, CU_DEVICE_ATTRIBUTE_CLOCK_RATE, dev);
+    info->clock_mhz = khz / 1000;
+    d->cuDeviceGetAttribute(&info->max_threads_per_block, CU_DEVICE_ATTRIBUTE_MAX_THREADS_PER_BLOCK, dev);
+    size_t total = 0;
+    d->cuDeviceTotalMem(&total, dev);
+    info->total_memory = total;
+    info->max_alloc = total; // CUDA has no per-allocation cap below the device size
+    d->cuDriverGetVersion(&info->driver_version);
+    return CLODE_OK;
+}
+
+int clode_compile(const clode_program_desc *desc, void **cubin, size_t *cubin_size, char **log)
+{
+    ProgramSpec s;
+    int rc = parse_desc(desc, s);
+    if (rc) return rc;
+    std::vector<char> bin;
+    std::string lg;
+    rc = compile_spec(s, bin, lg);
+    if (log) {
+        const std::string &text = rc ? g_error : lg;
+        *log = (char *)std::malloc(text.size() + 1);
+        std::memcpy(*log, text.c_str(), text.size() + 1);
+    }
+    if (rc) return rc;
+    if (cubin && cubin_size) {
+        *cubin = std::malloc(bin.size());
+        std::memcpy(*cubin, bin.data(), bin.size());
+        *cubin_size = bin.size();
+    }
+    return CLODE_OK;
+}
+
+int clode_program_source(const clode_program_desc *desc, char **source)
+{
+    if (!source) return fail(CLODE_ERR_INVALID, "source is null");
+    ProgramSpec s;
+    int rc = parse_desc(desc, s);
+    if (rc) return rc;
+    std::string text = full_source(s);
+    *source = (char *)std::malloc(text.size() + 1);
+    std::memcpy(*source, text.c_str(), text.size() + 1);
+    return CLODE_OK;
+}
+
+int clode_sim_create(int device, clode_sim **out)
+{
+    if (!out) return fail(CLODE_ERR_INVALID, "out is null");
+    *out = nullptr;
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (!d) return fail(CLODE_ERR_NO_DRIVER, why);
+    int count = 0;
+    d->cuDeviceGetCount(&count);
+    if (device < 0 || device >= count)
+        return fail(CLODE_ERR_INVALID, "device " + std::to_string(device) + " out of range (" + std::to_string(count) + " CUDA devices)");
+    clode_sim *s = new clode_sim();
+    s->d = d;
+    s->device = device;
+    CUresult r = d->cuDeviceGet(&s->dev, device);
+    if (r == CUDA_SUCCESS) r = d->cuDevicePrimaryCtxRetain(&s->ctx, s->dev);
+    if (r != CUDA_SUCCESS) {
+        int rc = fail(CLODE_ERR_CUDA, "cuDevicePrimaryCtxRetain: " + cu_error(d, r));
+        delete s;
+        return rc;
+    }
+    d->cuDeviceGetAttribute(&s->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, s->dev);
+    d->cuDeviceTotalMem(&s->total_mem, s->dev);
+    clode_sim::Scope scope(s);
+    r = d->cuStreamCreate(&s->stream, CU_STREAM_NON_BLOCKING);
+    if (r == CUDA_SUCCESS) r = d->cuEventCreate(&s->ev0, CU_EVENT_DEFAULT);
+    if (r == CUDA_SUCCESS) r = d->cuEventCreate(&s->ev1, CU_EVENT_DEFAULT);
+    if (r != CUDA_SUCCESS) {
+        int rc = fail(CLODE_ERR_CUDA, "stream/event creation: " + cu_error(d, r));
+        d->cuDevicePrimaryCtxRelease(s->dev);
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return CLODE_OK;
+}
+
+int clode_sim_destroy(clode_sim *s)
+{
+    if (!s) return CLODE_OK;
+    {
+        clode_sim::Scope scope(s);
+        s->d->cuStreamSynchronize(s->stream);
+        s->free_ensemble();
+        if (s->module) s->d->cuModuleUnload(s->module);
+        if (s->ev0) s->d->cuEventDestroy(s->ev0);
+        if (s->ev1) s->d->cuEventDestroy(s->ev1);
+        if (s->stream) s->d->cuStreamDestroy(s->stream);
+    }
+    s->d->cuDevicePrimaryCtxRelease(s->dev);
+    delete s;
+    return CLODE_OK;
+}
+
+int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    ProgramSpec spec;
+    int rc = parse_desc(desc, spec);
+    if (rc) return rc;
+    std::vector<char> cubin;
+    std::string log;
+    rc = compile_spec(spec, cubin, log);
+    s->build_log = rc ? g_error : log;
+    if (rc) return rc;
+
+    clode_sim::Scope scope(s);
+    const bool layout_changed = !s->built || spec.single != s->spec.single || spec.n_var != s->spec.n_var ||
+                                spec.n_par != s->spec.n_par || spec.n_aux != s->spec.n_aux;
+    if (s->module) {
+        s->d->cuStreamSynchronize(s->stream);
+        s->d->cuModuleUnload(s->module);
+        s->module = nullptr;
+    }
+    s->k_transient = s->k_init = s->k_features = s->k_trajectory = s->k_layout = nullptr;
+    s->built = false;
+    if ((rc = s->cu(s->d->cuModuleLoadData(&s->module, cubin.data()), "cuModuleLoadData"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_transient, s->module, "clode_transient"), "clode_transient"))) return rc;
+    if (spec.kernels & CLODE_KERNEL_FEATURES) {
+        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_init, s->module, "clode_initialize_observer"), "clode_initialize_observer"))) return rc;
+        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_features, s->module, "clode_features"), "clode_features"))) return rc;
+        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_layout, s->module, "clode_observer_layout"), "clode_observer_layout"))) return rc;
+        // ask the module how many observer-state rows it needs
+        CUdeviceptr tmp = 0;
+        if ((rc = s->cu(s->d->cuMemAlloc(&tmp, 16), "cuMemAlloc"))) return rc;
+        void *params[] = {&tmp};
+        rc = s->cu(s->d->cuLaunchKernel(s->k_layout, 1, 1, 1, 1, 1, 1, 0, s->stream, params, nullptr), "clode_observer_layout");
+        int host[3] = {0, 0, 0};
+        if (!rc) rc = s->cu(s->d->cuStreamSynchronize(s->stream), "clode_observer_layout");
+        if (!rc) rc = s->cu(s->d->cuMemcpyDtoH(host, tmp, sizeof host), "cuMemcpyDtoH");
+        s->d->cuMemFree(tmp);
+        if (rc) return rc;
+        s->od_nreal = host[0]; s->od_nuint = host[1]; s->two_pass = host[2];
+    }
+    if (spec.kernels & CLODE_KERNEL_TRAJECTORY) {
+        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_trajectory, s->module, "clode_trajectory"), "clode_trajectory"))) return rc;
+    }
+    s->n_features = observer_feature_count(spec.observer, spec.n_var, spec.n_aux, spec.n_store);
+    s->real_size = spec.single ? 4 : 8;
+    if (layout_changed) s->free_ensemble(); // precision / dimension change invalidates device data
+    // a different observer or event-list length changes the observer-state layout
+    if (s->built == false) {
+        s->release(s->od_real); s->release(s->od_uint); s->release(s->F);
+        s->observer_initialized = false;
+    }
+    s->spec = spec;
+    s->built = true;
+    return CLODE_OK;
+}
+
+int clode_sim_build_log(clode_sim *s, const char **log)
+{
+    if (!s || !log) return fail(CLODE_ERR_INVALID, "null argument");
+    *log = s->build_log.c_str();
+    return CLODE_OK;
+}
+
+int clode_sim_set_npts(clode_sim *s, size_t n_pts, double fill_dt)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built) return fail(CLODE_ERR_STATE, "set_npts: build the program first");
+    clode_sim::Scope scope(s);
+    const size_t rs = s->real_size;
+    int rc;
+    if (n_pts != s->n) {
+        s->free_ensemble();
+        s->n = n_pts;
+        if ((rc = s->alloc(s->x0, rs * s->spec.n_var * n_pts, "x0"))) return rc;
+        if ((rc = s->alloc(s->pars, rs * s->spec.n_par * n_pts, "pars"))) return rc;
+        if ((rc = s->alloc(s->xf, rs * s->spec.n_var * n_pts, "xf"))) return rc;
+        if ((rc = s->alloc(s->rng, 8 * 2 * n_pts, "rng"))) return rc;
+        if ((rc = s->alloc(s->dt, rs * n_pts, "dt"))) return rc;
+        if ((rc = s->alloc(s->tf, rs * n_pts, "tf"))) return rc;
+        if ((rc = s->alloc(s->steps, 4 * n_pts, "steps"))) return rc;
+        if ((rc = s->alloc(s->queue, 8, "queue"))) return rc;
+        if (n_pts) {
+            if ((rc = s->cu(s->d->cuMemsetD8Async(s->rng.ptr, 0, s->rng.bytes, s->stream), "memset rng"))) return rc;
+            if ((rc = s->cu(s->d->cuMemsetD8Async(s->xf.ptr, 0, s->xf.bytes, s->stream), "memset xf"))) return rc;
+            if ((rc = s->cu(s->d->cuMemsetD8Async(s->tf.ptr, 0, s->tf.bytes, s->stream), "memset tf"))) return rc;
+            if ((rc = s->cu(s->d->cuMemsetD8Async(s->steps.ptr, 0, s->steps.bytes, s->stream), "memset steps"))) return rc;
+        }
+    }
+    if (n_pts) {
+        std::vector<double> fill(n_pts, fill_dt);
+        if ((rc = s->cu(s->d->cuStreamSynchronize(s->stream), "sync"))) return rc;
+        if ((rc = s->upload_real(s->dt, fill.data(), n_pts, "dt"))) return rc;
+    }
+    return CLODE_OK;
+}
+
+int clode_sim_get_npts(clode_sim *s, size_t *n_pts)
+{
+    if (!s || !n_pts) return fail(CLODE_ERR_INVALID, "null argument");
+    *n_pts = s->n;
+    return CLODE_OK;
+}
+
+int clode_sim_set_x0(clode_sim *s, const double *x0, size_t count)
+{
+    if (!s || !x0) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != s->n * s->spec.n_var) return fail(CLODE_ERR_INVALID, "set_x0: expected nPts*nVar elements");
+    clode_sim::Scope scope(s);
+    return s->upload_real(s->x0, x0, count, "set_x0");
+}
+
+int clode_sim_set_pars(clode_sim *s, const double *pars, size_t count)
+{
+    if (!s || (!pars && count)) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != s->n * s->spec.n_par) return fail(CLODE_ERR_INVALID, "set_pars: expected nPts*nPar elements");
+    clode_sim::Scope scope(s);
+    return s->upload_real(s->pars, pars, count, "set_pars");
+}
+
+int clode_sim_set_dt(clode_sim *s, const double *dt, size_t count)
+{
+    if (!s || !dt) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != s->n) return fail(CLODE_ERR_INVALID, "set_dt: expected nPts elements");
+    clode_sim::Scope scope(s);
+    return s->upload_real(s->dt, dt, count, "set_dt");
+}
+
+int clode_sim_set_tspan(clode_sim *s, double t0, double t1)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    s->t0 = t0;
+    s->t1 = t1;
+    return CLODE_OK;
+}
+
+int clode_sim_set_solver_params(clode_sim *s, const clode_solver_params *sp)
+{
+    if (!s || !sp) return fail(CLODE_ERR_INVALID, "null argument");
+    s->sp = *sp;
+    return CLODE_OK;
+}
+
+int clode_sim_set_observer_params(clode_sim *s, const clode_observer_params *op)
+{
+    if (!s || !op) return fail(CLODE_ERR_INVALID, "null argument");
+    s->op = *op;
+    return CLODE_OK;
+}
+
+int clode_sim_seed_rng(clode_sim *s, int64_t seed, uint64_t offset, uint64_t n_global)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (s->n == 0) return fail(CLODE_ERR_STATE, "seed_rng: nPts == 0");
+    if (n_global == 0) n_global = s->n;
+    std::vector<uint64_t> st(2 * s->n);
+    for (size_t i = 0; i < s->n; ++i) {
+        st[i] = (uint64_t)(seed + (int64_t)(offset + i));
+        st[s->n + i] = (uint64_t)(seed + (int64_t)(n_global + offset + i));
+    }
+    return clode_sim_set_rng_state(s, st.data(), st.size());
+}
+
+int clode_sim_set_rng_state(clode_sim *s, const uint64_t *state, size_t count)
+{
+    if (!s || !state) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != 2 * s->n) return fail(CLODE_ERR_INVALID, "set_rng_state: expected 2*nPts words");
+    clode_sim::Scope scope(s);
+    return s->cu(s->d->cuMemcpyHtoD(s->rng.ptr, state, 8 * count), "set_rng_state");
+}
+
+int clode_sim_get_rng_state(clode_sim *s, uint64_t *state, size_t count)
+{
+    if (!s || !state) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != 2 * s->n) return fail(CLODE_ERR_INVALID, "get_rng_state: expected 2*nPts words");
+    clode_sim::Scope scope(s);
+    return s->cu(s->d->cuMemcpyDtoH(state, s->rng.ptr, 8 * count), "get_rng_state");
+}
+
+int clode_sim_transient(clode_sim *s)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built) return fail(CLODE_ERR_STATE, "transient: program not built");
+    clode_sim::Scope scope(s);
+    return s->launch(s->k_transient, "clode_transient", true, true);
+}
+
+static int ensure_feature_buffers(clode_sim *s)
+{
+    // CLODEfeatures::resizeFeaturesVariables (CLODEfeatures.cpp:143-178)
+    const size_t rs = s->real_size;
+    const size_t f_bytes = rs * (size_t)s->n_features * s->n;
+    const size_t r_bytes = rs * (size_t)s->od_nreal * s->n, u_bytes = 4 * (size_t)s->od_nuint * s->n;
+    if (s->F.bytes != f_bytes || s->od_real.bytes != r_bytes || s->od_uint.bytes != u_bytes || !s->F.ptr) {
+        int rc;
+        if ((rc = s->alloc(s->F, f_bytes, "F"))) return rc;
+        if ((rc = s->alloc(s->od_real, r_bytes, "observer data"))) return rc;
+        if ((rc = s->alloc(s->od_uint, u_bytes, "observer data"))) return rc;
+        s->observer_initialized = false;
+    }
+    return CLODE_OK;
+}
+
+int clode_sim_initialize_observer(clode_sim *s)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built || !s->k_init) return fail(CLODE_ERR_STATE, "initialize_observer: features kernels not built");
+    clode_sim::Scope scope(s);
+    int rc = ensure_feature_buffers(s);
+    if (rc) return rc;
+    rc = s->launch(s->k_init, "clode_initialize_observer", true, true);
+    if (!rc) s->observer_initialized = true;
+    return rc;
+}
+
+int clode_sim_features(clode_sim *s, int initialize)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built || !s->k_features) return fail(CLODE_ERR_STATE, "features: features kernels not built");
+    clode_sim::Scope scope(s);
+    int rc = ensure_feature_buffers(s);
+    if (rc) return rc;
+    if (initialize == 1) s->observer_initialized = false;
+    // CLODEfeatures::features() (CLODEfeatures.cpp:222-258): warm-up/initialise if needed, then the features pass;
+    // both launches are inside the timed region
+    bool first = true;
+    if (!s->observer_initialized) {
+        if ((rc = s->launch(s->k_init, "clode_initialize_observer", true, false))) return rc;
+        s->observer_initialized = true;
+        first = false;
+    }
+    return s->launch(s->k_features, "clode_features", first, true);
+}
+
+int clode_sim_observer_initialized(clode_sim *s, int *flag)
+{
+    if (!s || !flag) return fail(CLODE_ERR_INVALID, "null argument");
+    *flag = s->observer_initialized ? 1 : 0;
+    return CLODE_OK;
+}
+
+int clode_sim_trajectory(clode_sim *s)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built || !s->k_trajectory) return fail(CLODE_ERR_STATE, "trajectory: trajectory kernel not built");
+    if (s->n == 0) return fail(CLODE_ERR_STATE, "trajectory: nPts == 0");
+    clode_sim::Scope scope(s);
+    // CLODEtrajectory::resizeTrajectoryVariables (CLODEtrajectory.cpp:45-95); one extra row because the
+    // kernel can write row index max_store
+    const size_t rows = (size_t)s->sp.max_store + 1;
+    const size_t rs = s->real_size;
+    int rc;
+    if (rows != s->tr_rows || !s->tr_t.ptr) {
+        const size_t nv = s->spec.n_var, na = s->spec.n_aux;
+        const size_t biggest = rs * rows * s->n * std::max<size_t>(nv, std::max<size_t>(na, 1));
+        if (biggest > s->total_mem || rs * rows * s->n * (1 + 2 * nv + na) > s->total_mem)
+            return fail(CLODE_ERR_MEMORY, "nPts*nStoreMax*nVar*realSize or nPts*nStoreMax*nAux*realSize is too big");
+        if ((rc = s->alloc(s->tr_t, rs * rows * s->n, "t"))) return rc;
+        if ((rc = s->alloc(s->tr_x, rs * rows * s->n * nv, "x"))) return rc;
+        if ((rc = s->alloc(s->tr_dx, rs * rows * s->n * nv, "dx"))) return rc;
+        if ((rc = s->alloc(s->tr_aux, rs * std::max<size_t>(rows * s->n * na, 1), "aux"))) return rc;
+        if ((rc = s->alloc(s->n_stored, 4 * s->n, "nStored"))) return rc;
+        s->tr_rows = rows;
+    }
+    return s->launch(s->k_trajectory, "clode_trajectory", true, true);
+}
+
+int clode_sim_shift_x0(clode_sim *s)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (s->n == 0) return CLODE_OK;
+    clode_sim::Scope scope(s);
+    int rc = s->cu(s->d->cuMemcpyDtoDAsync(s->x0.ptr, s->xf.ptr, s->x0.bytes, s->stream), "shift_x0");
+    if (rc) return rc;
+    return s->cu(s->d->cuStreamSynchronize(s->stream), "shift_x0");
+}
+
+static Buffer *pick_buffer(clode_sim *s, int which, int *elem)
+{
+    int e = (int)s->real_size;
+    Buffer *b = nullptr;
+    switch (which) {
+    case CLODE_BUF_X0: b = &s->x0; break;
+    case CLODE_BUF_PARS: b = &s->pars; break;
+    case CLODE_BUF_XF: b = &s->xf; break;
+    case CLODE_BUF_DT: b = &s->dt; break;
+    case CLODE_BUF_TF: b = &s->tf; break;
+    case CLODE_BUF_F: b = &s->F; break;
+    case CLODE_BUF_T: b = &s->tr_t; break;
+    case CLODE_BUF_X: b = &s->tr_x; break;
+    case CLODE_BUF_DX: b = &s->tr_dx; break;
+    case CLODE_BUF_AUX: b = &s->tr_aux; break;
+    case CLODE_BUF_RNG: b = &s->rng; e = 8; break;
+    case CLODE_BUF_STEPS: b = &s->steps; e = 4; break;
+    case CLODE_BUF_NSTORED: b = &s->n_stored; e = 4; break;
+    }
+    if (elem) *elem = e;
+    return b;
+}
+
+int clode_sim_get(clode_sim *s, int which, double *out, size_t count)
+{
+    if (!s || (!out && count)) return fail(CLODE_ERR_INVALID, "null argument");
+    if (which < CLODE_BUF_X0 || which > CLODE_BUF_AUX) return fail(CLODE_ERR_INVALID, "get: not a real-valued buffer");
+    int elem;
+    Buffer *b = pick_buffer(s, which, &elem);
+    if (!b->ptr && count) return fail(CLODE_ERR_STATE, "get: buffer not allocated yet (run the simulation first)");
+    clode_sim::Scope scope(s);
+    return s->download_real(*b, out, count, "get");
+}
+
+int clode_sim_get_n_stored(clode_sim *s, int *out, size_t count)
+{
+    if (!s || !out) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != s->n || !s->n_stored.ptr) return fail(CLODE_ERR_STATE, "get_n_stored: run trajectory() first / wrong count");
+    clode_sim::Scope scope(s);
+    return s->cu(s->d->cuMemcpyDtoH(out, s->n_stored.ptr, 4 * count), "get_n_stored");
+}
+
+int clode_sim_get_steps(clode_sim *s, uint32_t *out, size_t count)
+{
+    if (!s || !out) return fail(CLODE_ERR_INVALID, "null argument");
+    if (count != s->n || !s->steps.ptr) return fail(CLODE_ERR_STATE, "get_steps: wrong count");
+    clode_sim::Scope scope(s);
+    return s->cu(s->d->cuMemcpyDtoH(out, s->steps.ptr, 4 * count), "get_steps");
+}
+
+int clode_sim_n_features(clode_sim *s, int *n_features)
+{
+    if (!s || !n_features) return fail(CLODE_ERR_INVALID, "null argument");
+    *n_features = s->n_features;
+    return CLODE_OK;
+}
+
+int clode_sim_device_buffer(clode_sim *s, int which, uint64_t *device_ptr, size_t *bytes, int *elem_size)
+{
+    if (!s || !device_ptr) return fail(CLODE_ERR_INVALID, "null argument");
+    int elem;
+    Buffer *b = pick_buffer(s, which, &elem);
+    if (!b) return fail(CLODE_ERR_INVALID, "device_buffer: unknown buffer id");
+    *device_ptr = (uint64_t)b->ptr;
+    if (bytes) *bytes = b->bytes;
+    if (elem_size) *elem_size = elem;
+    return CLODE_OK;
+}
+
+int clode_sim_last_kernel_ms(clode_sim *s, float *ms)
+{
+    if (!s || !ms) return fail(CLODE_ERR_INVALID, "null argument");
+    *ms = s->last_ms;
+    return CLODE_OK;
+}
+
+int clode_sim_launch_count(clode_sim *s, uint64_t *launches)
+{
+    if (!s || !launches) return fail(CLODE_ERR_INVALID, "null argument");
+    *launches = s->launches;
+    return CLODE_OK;
+}
+
+int clode_sim_kernel_info(clode_sim *s, int kernel, clode_kernel_info *info)
+{
+    if (!s || !info) return fail(CLODE_ERR_INVALID, "null argument");
+    if (!s->built) return fail(CLODE_ERR_STATE, "kernel_info: program not built");
+    CUfunction f = kernel == CLODE_KERNEL_TRANSIENT ? s->k_transient
+                 : kernel == CLODE_KERNEL_FEATURES ? s->k_features
+                 : kernel == CLODE_KERNEL_TRAJECTORY ? s->k_trajectory : nullptr;
+    if (!f) return fail(CLODE_ERR_INVALID, "kernel_info: kernel not part of this program");
+    clode_sim::Scope scope(s);
+    std::memset(info, 0, sizeof *info);
+    s->d->cuFuncGetAttribute(&info->registers, CU_FUNC_ATTRIBUTE_NUM_REGS, f);
+    s->d->cuFuncGetAttribute(&info->local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
+    s->d->cuFuncGetAttribute(&info->shared_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, f);
+    s->d->cuFuncGetAttribute(&info->const_bytes, CU_FUNC_ATTRIBUTE_CONST_SIZE_BYTES, f);
+    s->d->cuFuncGetAttribute(&info->max_threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, f);
+    info->block_size = s->spec.block;
+    s->d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&info->blocks_per_sm, f, s->spec.block, 0);
+    unsigned grid = 0;
+    if (s->n) s->grid_for(f, grid);
+    info->grid_size = (int)grid;
+    return CLODE_OK;
+}
+
+} // extern "C"
