@@ -25,7 +25,15 @@
 #define CLODE_MIN_BLOCKS 1
 #endif
 
-// Launch arguments, one struct by value (lands in the constant bank; uniform loads).
+// Launch arguments: one struct in __constant__ memory (`clode_args`), written by the host
+// with an in-stream copy before each launch; every field is a warp-uniform constant-bank load.
+// NOTE: deliberately NOT a by-value kernel parameter.  With a by-value struct larger than
+// ~128 bytes (with or without __grid_constant__) NVVM 12.9 keeps the argument in param space
+// behind a pointer and then MISCOMPILES the time loop: the floating-point exit test
+// `t <= t_end` is dropped (the loop runs max_steps iterations) and t is advanced once.
+// Found on the first GPU run by the parity tests; reproduced with a 20-line kernel
+// (profiles/r01_nvvm_byval_param_miscompile.md).  __constant__ and global-pointer arguments
+// compile correctly.
 // Scalars travel as double and are narrowed on the device when realtype is float — the
 // same round-to-nearest conversion the reference does on the host (CLODE.cpp:292-300, 377-394).
 struct KernelArgs {
@@ -47,6 +55,8 @@ struct KernelArgs {
     int *n_stored;                 // [n]
     unsigned long long *queue;     // work-queue head (CLODE_WORK_QUEUE)
 };
+
+extern "C" __constant__ KernelArgs clode_args;
 
 CLODE_DEV SolverParams solver_params(const KernelArgs &a)
 {
@@ -157,8 +167,9 @@ CLODE_DEV WorkSource work_source(const KernelArgs &a)
 
 // ------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_transient(const __grid_constant__ KernelArgs a)
+clode_transient()
 {
+    const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);
@@ -179,8 +190,9 @@ clode_transient(const __grid_constant__ KernelArgs a)
 #ifdef CLODE_WITH_FEATURES
 // ------------------------------------------------------------------------------------------
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_initialize_observer(const __grid_constant__ KernelArgs a)
+clode_initialize_observer()
 {
+    const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
     const ObserverParams op = observer_params(a);
     const realtype t_end = (realtype)a.t1;
@@ -217,8 +229,9 @@ clode_initialize_observer(const __grid_constant__ KernelArgs a)
 }
 
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_features(const __grid_constant__ KernelArgs a)
+clode_features()
 {
+    const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
     const ObserverParams op = observer_params(a);
     const realtype t_end = (realtype)a.t1;
@@ -293,8 +306,9 @@ CLODE_DEV void store_point(const Instance &I, const KernelArgs &a, const size_t 
 }
 
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_trajectory(const __grid_constant__ KernelArgs a)
+clode_trajectory()
 {
+    const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);

@@ -292,6 +292,7 @@ struct clode_sim {
     bool built = false;
     std::string build_log;
     CUmodule module = nullptr;
+    CUdeviceptr args_symbol = 0; // __constant__ KernelArgs clode_args
     CUfunction k_transient = nullptr, k_init = nullptr, k_features = nullptr, k_trajectory = nullptr, k_layout = nullptr;
     int od_nreal = 0, od_nuint = 0, two_pass = 0;
     int n_features = 0;
@@ -412,11 +413,13 @@ struct clode_sim {
             if ((rc = cu(d->cuMemsetD8Async(queue.ptr, 0, 8, stream), "reset work queue"))) return rc;
         }
         KernelArgs a = args();
-        void *params[] = {&a};
         unsigned grid = 1;
         if ((rc = grid_for(f, grid))) return rc;
+        // arguments go to the module's __constant__ block, ordered in-stream before the launch
+        // (pageable source: the driver stages the bytes before cuMemcpyHtoDAsync returns)
+        if ((rc = cu(d->cuMemcpyHtoDAsync(args_symbol, &a, sizeof a, stream), "upload kernel arguments"))) return rc;
         if (first && (rc = cu(d->cuEventRecord(ev0, stream), "cuEventRecord"))) return rc;
-        if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, 0, stream, params, nullptr), what))) return rc;
+        if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, 0, stream, nullptr, nullptr), what))) return rc;
         ++launches;
         if (last) {
             if ((rc = cu(d->cuEventRecord(ev1, stream), "cuEventRecord"))) return rc;
@@ -585,6 +588,11 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
     s->k_transient = s->k_init = s->k_features = s->k_trajectory = s->k_layout = nullptr;
     s->built = false;
     if ((rc = s->cu(s->d->cuModuleLoadData(&s->module, cubin.data()), "cuModuleLoadData"))) return rc;
+    {
+        size_t sym_bytes = 0;
+        if ((rc = s->cu(s->d->cuModuleGetGlobal(&s->args_symbol, &sym_bytes, s->module, "clode_args"), "clode_args"))) return rc;
+        if (sym_bytes != sizeof(KernelArgs)) return fail(CLODE_ERR_BUILD, "KernelArgs layout mismatch between host and device");
+    }
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_transient, s->module, "clode_transient"), "clode_transient"))) return rc;
     if (spec.kernels & CLODE_KERNEL_FEATURES) {
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_init, s->module, "clode_initialize_observer"), "clode_initialize_observer"))) return rc;

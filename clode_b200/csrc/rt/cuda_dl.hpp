@@ -30,7 +30,7 @@ namespace clode {
     X(cuMemHostAlloc) X(cuMemFreeHost)                                                            \
     X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize)                                   \
     X(cuEventCreate) X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) \
-    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction)                                  \
+    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuModuleGetGlobal)                                  \
     X(cuFuncGetAttribute) X(cuFuncSetAttribute) X(cuLaunchKernel)                                 \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor)
 

@@ -3,7 +3,8 @@ plus a rough Lorenz dopri5 timing.  Scratch diagnostics, not a test."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests.problems import ensemble, rhs_source
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from problems import ensemble, rhs_source
 from oracle.common import Config, Solver, Observer, seed_states, MODELS
 from oracle import restate
 from clode_b200 import _rt
