@@ -1,0 +1,84 @@
+"""Accuracy and special values of the portable math header used by the bit-exact tier
+(clode_b200/csrc/device/pm_math.h) against numpy/glibc.  CPU only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def pm():
+    out = os.path.join(REPO, "oracle", "_build", "pm_probe.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{REPO}/clode_b200/csrc/device",
+                    os.path.join(HERE, "emu", "pm_probe.c"), "-o", out], check=True)
+    return ctypes.CDLL(out)
+
+
+def _call1(fn, x):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.empty_like(x)
+    fn(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), x.size)
+    return y
+
+
+def _ulp_err(got, want):
+    return np.abs(got - want) / np.spacing(np.abs(want))
+
+
+def test_exp_log_sin_cos_accuracy(pm):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-1, 1, 100000), rng.normal(0, 1e-8, 1000)])
+    assert _ulp_err(_call1(pm.probe_exp, x), np.exp(x)).max() <= 2.0
+    x = np.concatenate([10.0 ** rng.uniform(-300, 300, 200000), rng.uniform(0.5, 2.0, 100000), [5e-324, 1e-310]])
+    want = np.log(x)
+    err = np.abs(_call1(pm.probe_log, x) - want) / np.maximum(np.spacing(np.abs(want)), 1e-300)
+    assert err.max() <= 2.0
+    x = np.concatenate([rng.uniform(-50, 50, 200000), rng.uniform(-1e4, 1e4, 50000)])
+    # absolute-error bound near zeros of sin/cos (Cody-Waite reduction keeps ~1e-16 * |n| absolute error)
+    for fn, ref in ((pm.probe_sin, np.sin), (pm.probe_cos, np.cos)):
+        got, want = _call1(fn, x), ref(x)
+        assert np.max(np.abs(got - want)) <= 4e-16
+        big = np.abs(want) > 0.1
+        assert _ulp_err(got[big], want[big]).max() <= 2.0
+
+
+def test_pow_accuracy_inside_opencl_bound(pm):
+    """pow(x, y) error <= 2 + |y ln x| ulp; OpenCL C 1.2 allows 16 ulp for pow"""
+    rng = np.random.default_rng(1)
+    x = 10.0 ** rng.uniform(-12, 12, 200000)
+    y = rng.uniform(-3, 3, x.size)
+    got = np.empty_like(x)
+    pm.probe_pow(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p),
+                 got.ctypes.data_as(ctypes.c_void_p), x.size)
+    want = np.power(x, y)
+    err = _ulp_err(got, want)
+    assert np.all(err <= 2.0 + np.abs(y * np.log(x)))
+    ctrl = np.abs(y * np.log(x)) < 5  # the step-size controller's operating range
+    assert err[ctrl].max() <= 7.0
+
+
+def test_special_values(pm):
+    inf, nan = np.inf, np.nan
+    assert np.array_equal(_call1(pm.probe_exp, [0.0, -inf, inf, 710.0, -750.0]), [1.0, 0.0, inf, inf, 0.0])
+    assert np.isnan(_call1(pm.probe_exp, [nan]))[0]
+    got = _call1(pm.probe_log, [1.0, 0.0, -0.0, inf])
+    assert np.array_equal(got, [0.0, -inf, -inf, inf])
+    assert np.isnan(_call1(pm.probe_log, [-1.0, nan])).all()
+
+    def p(a, b):
+        a, b = np.array([a], np.float64), np.array([b], np.float64)
+        out = np.empty(1)
+        pm.probe_pow(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                     out.ctypes.data_as(ctypes.c_void_p), 1)
+        return out[0]
+
+    assert p(2.0, 0.0) == 1.0 and p(nan, 0.0) == 1.0 and p(1.0, nan) == 1.0
+    assert p(inf, 0.2) == inf and p(0.0, 0.2) == 0.0 and p(0.0, -1.0) == inf
+    assert p(-2.0, 3.0) == pytest.approx(-8.0) and p(-2.0, 2.0) == pytest.approx(4.0) and np.isnan(p(-2.0, 0.5))
+    assert p(4.0, 0.5) == pytest.approx(2.0, rel=1e-15) and p(2.0, 10.0) == pytest.approx(1024.0, rel=1e-15)

@@ -1,0 +1,112 @@
+"""The C-ABI runtime library: loads without a GPU, exports every symbol include/clode_rt.h
+declares, NVRTC-compiles programs for sm_100a without a GPU, and fails LOUDLY (no CPU fallback)
+when asked to compute without a CUDA driver.  CPU only; no compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "clode_rt.h")).read()
+    return sorted(set(re.findall(r"CLODE_API\s+[\w\s\*]+?\b(clode_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_symbols()
+    for must in ["clode_sim_create", "clode_sim_build", "clode_sim_transient", "clode_sim_features",
+                 "clode_sim_initialize_observer", "clode_sim_trajectory", "clode_sim_shift_x0", "clode_sim_get",
+                 "clode_sim_seed_rng", "clode_compile", "clode_last_error", "clode_device_count"]:
+        assert must in names
+    assert len(names) >= 35
+
+
+def test_library_exports_every_declared_symbol(rt):
+    lib = rt.lib()
+    out = subprocess.run(["nm", "-D", "--defined-only", rt.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (clode_\w+)", out))
+    missing = [n for n in declared_symbols() if n not in exported]
+    assert not missing, missing
+    for n in declared_symbols():
+        assert getattr(lib, n) is not None
+
+
+def test_library_has_no_link_time_cuda_dependency(rt):
+    out = subprocess.run(["ldd", rt.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda" not in out and "libnvrtc" not in out and "libtorch" not in out
+
+
+def test_header_is_plain_c():
+    src = '#include "clode_rt.h"\nint main(void){ clode_program_desc d; (void)d; return sizeof(clode_solver_params) == 48 ? 0 : 1; }\n'
+    exe = os.path.join(REPO, "oracle", "_build", "abi_c_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{REPO}/include", "-x", "c", "-", "-o", exe],
+                   input=src, text=True, check=True)
+    assert subprocess.run([exe]).returncode == 0
+
+
+def _have_driver(rt):
+    try:
+        return rt.device_count() > 0
+    except rt.RtError:
+        return False
+
+
+def test_compute_without_driver_fails_loudly(rt):
+    if _have_driver(rt):
+        pytest.skip("a CUDA driver is present")
+    with pytest.raises(rt.RtError) as e:
+        rt.device_count()
+    assert e.value.code == 2 and "libcuda" in str(e.value)
+    from problems import rhs_source
+    with pytest.raises(rt.RtError) as e:
+        rt.Sim(rt.Program(rhs_source("lorenz63"), "rk4", 3, 3, 1))
+    assert e.value.code == 2
+
+
+@pytest.mark.parametrize("stepper", ["euler", "heun", "rk4", "bs23", "dopri5"])
+@pytest.mark.parametrize("observer", ["basic", "basicall", "localmax", "nhood1", "nhood2", "thresh2"])
+def test_nvrtc_compiles_every_stepper_observer_pair(rt, stepper, observer, tmp_path):
+    from problems import rhs_source
+    prog = rt.Program(rhs_source("lorenz63"), stepper, 3, 3, 1, observer=observer, n_store_events=2)
+    cubin, log = rt.compile_program(prog)
+    assert cubin[:4] == b"\x7fELF"
+    p = tmp_path / "k.cubin"
+    p.write_bytes(cubin)
+    usage = subprocess.run(["cuobjdump", "--dump-resource-usage", str(p)], capture_output=True, text=True).stdout
+    for k in ("clode_transient", "clode_initialize_observer", "clode_features", "clode_trajectory"):
+        assert k in usage
+    listing = subprocess.run(["cuobjdump", "-lelf", str(p)], capture_output=True, text=True).stdout
+    assert "sm_100a" in listing, listing
+    # the user RHS must be inlined into the kernels: no separate device function in the cubin
+    functions = re.findall(r"Function (\w+):", usage)
+    assert sorted(functions) == sorted(["clode_transient", "clode_initialize_observer", "clode_features",
+                                        "clode_trajectory", "clode_observer_layout"]), functions
+
+
+def test_nvrtc_other_variants(rt):
+    from problems import rhs_source
+    rt.compile_program(rt.Program(rhs_source("lactotroph_noise"), "seuler", 4, 4, 1, 1, observer="basicall"))
+    rt.compile_program(rt.Program(rhs_source("vanderpol"), "dopri5", 2, 1, observer="thresh2", single_precision=True))
+    rt.compile_program(rt.Program(rhs_source("lactotroph"), "bs23", 4, 3, 1, observer="thresh2", bit_exact=True))
+    rt.compile_program(rt.Program(rhs_source("chay_keizer"), "rk4", 3, 3, work_queue=True, kernels=rt.KERNEL_TRAJECTORY))
+    src = rt.program_source(rt.Program(rhs_source("lorenz63"), "rk4", 3, 3, 1))
+    assert "getRHS" in src and "-DEXPLICIT_RK4" in src and "clode_transient" in src
+
+
+def test_build_errors_are_reported_with_the_compiler_log(rt):
+    with pytest.raises(rt.RtError) as e:
+        rt.compile_program(rt.Program("void getRHS(const realtype t, const realtype x_[], const realtype p_[], "
+                                      "realtype dx_[], realtype aux_[], const realtype w_[]) { dx_[0] = undefined_symbol; }",
+                                      "rk4", 1, 1))
+    assert e.value.code == 4 and "undefined_symbol" in str(e.value)
+    with pytest.raises(rt.RtError) as e:
+        rt.compile_program(rt.Program("", "rk45", 1, 1))
+    assert e.value.code == 1 and "unknown stepper" in str(e.value)
+    with pytest.raises(rt.RtError):
+        rt.compile_program(rt.Program("", "rk4", 2, 1, observer="thresh2", f_var_ix=5))
