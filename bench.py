@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the ensemble-ODE hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C3|C5]
+
+Workload (default C2 = BASELINE.json configs[1]): Lorenz system, `features` kernel, dopri5,
+observer `basic`, 2^20 parameter sets PER GPU (weak scaling: the global r-grid is N*2^20 points,
+rank g integrates the contiguous slice [g*2^20, (g+1)*2^20)), double precision, t in [0,100],
+dt0 = 0.01, dtmax = 1, abstol = reltol = 1e-6.  One "step" = one pass of the hot
+path (initializeObserver + features kernels) over the rank's ensemble.
+
+metric  = accepted ODE instance-steps per second, whole job (sum over ranks / max-over-ranks time)
+value   : inputs resident in HBM, kernel time by CUDA events on the launch stream
+e2e     : the same metric through the public C-ABI call sequence with HOST buffers — per step
+          H2D of x0/pars/dt from pinned memory, the kernels, D2H of the feature matrix
+roofline: FP64 FMA pipe. achieved = 283 algorithmic flop per accepted Lorenz-dopri5 step
+          (clode_b200/flops.py) x steps / kernel time; peak = DFMA micro-benchmark measured
+          on this GPU in this run (MEASURED_PEAKS.json has no FP64 entry), nominal quoted beside it.
+cpu_baseline / --impl reference: the reference's own kernel sources compiled as host C
+          (oracle/_ref, OpenMP over all host cores) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+N_PER_GPU = 1 << 20
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: SMs x FP64 lanes x 2 x max clock
+
+
+# ------------------------------------------------------------------------------------------------
+def workload(name: str, n_total: int, lo: int, hi: int):
+    """inputs of instances [lo, hi) of a global ensemble of n_total (variable-major, float64)"""
+    from clode_b200.flops import flops_per_step
+
+    n = hi - lo
+    frac = (np.arange(lo, hi, dtype=np.float64)) / max(n_total - 1, 1)
+    if name == "C2":
+        w = dict(model="lorenz63", stepper="dopri5", observer="basic", kind="features", tspan=(0.0, 100.0),
+                 solver=dict(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, max_steps=10000000),
+                 observer_params=dict(max_event_count=10000),
+                 pars=np.concatenate([0.5 + 59.5 * frac, np.full(n, 10.0), np.full(n, 8.0 / 3.0)]),
+                 x0=np.ones(3 * n), desc="C2: Lorenz features, dopri5, observer basic, 2^20 parameter sets per GPU, f64")
+    elif name == "C3":
+        # 1024 x 1024 (gcal x gbk) grid, flattened row-major; bs23 + thresh2 (two-pass)
+        side = int(round(n_total ** 0.5))
+        idx = np.arange(lo, hi)
+        gcal = 0.5 + 3.5 * (idx // side) / max(side - 1, 1)
+        gbk = 2.0 * (idx % side) / max(side - 1, 1)
+        w = dict(model="lactotroph", stepper="bs23", observer="thresh2", kind="features", tspan=(0.0, 10000.0),
+                 solver=dict(dt=0.1, dtmax=100.0, abstol=1e-6, reltol=1e-4, max_steps=10000000),
+                 observer_params=dict(max_event_count=100000, x_up_threshold=0.3, x_down_threshold=0.2),
+                 pars=np.concatenate([gcal, np.full(n, 3.0), gbk]),
+                 x0=np.concatenate([np.full(n, -60.0), np.zeros(n), np.zeros(n), np.full(n, 0.1)]),
+                 desc="C3: lactotroph thresh2 features, bs23, 1024x1024 grid per GPU, f64")
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    w["flops_per_step"] = flops_per_step(w["stepper"], w["model"])
+    return w
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(wname: str, n_total: int, steps: int, warmup: int, stride: int = 64):
+    """the reference's own kernels on the host cores (oracle/_ref; falls back to the C port)"""
+    from oracle import ref, restate
+    from oracle.common import Config, Observer, Solver, seed_states
+
+    w = workload(wname, n_total, 0, N_PER_GPU)
+    cfg = Config(w["model"], w["stepper"], w["observer"], contract="fast")
+    if os.path.exists(ref.so_path(cfg)) or ref.reference_available():
+        lib, kind = ref.RefLib(cfg), "reference"
+    else:
+        lib, kind = restate.OracleLib(cfg), "port"
+    nv = lib.n_var
+    sel = np.arange(0, N_PER_GPU, stride)
+    n = sel.size
+    x0 = w["x0"].reshape(nv, -1)[:, sel].ravel()
+    pars = w["pars"].reshape(lib.n_par, -1)[:, sel].ravel()
+    sp, op = Solver(**w["solver"]), Observer(**w["observer_params"])
+    cores = os.cpu_count() or 1
+    step_row = {"basic": 5}.get(w["observer"], lib.n_feat - (1 if w["observer"] in ("basicall", "localmax") else 4))
+    times, total = [], 0
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = lib.features(w["tspan"], x0, pars, sp, op, np.full(n, sp.dt), seed_states(1, n), nthreads=cores)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+            total += int(r["F"].reshape(lib.n_feat, n)[step_row].sum())
+    value = total / sum(times)
+    sample = f"every {stride}th instance of the N=1 workload ({n} instances), {steps} passes, OpenMP {cores} threads, gcc -O3 -march=x86-64-v3"
+    return dict(value=value, unit="instance-steps/s", cores=cores, kind=kind, sample=sample), sum(times) / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms = cpu_reference(args.workload, N_PER_GPU * args.gpus, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": base["value"],
+            "unit": "instance-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload(args.workload, N_PER_GPU, 0, 1)["desc"],
+                                            "note": "CPU arm runs a bounded sample; the metric is per instance-step"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "instance-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+
+    from clode_b200 import _rt, build
+    from problems import rhs_source
+    from oracle.common import MODELS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    build.build_runtime()
+    n = N_PER_GPU if args.npts <= 0 else args.npts
+    n_total = n * world
+    w = workload(args.workload, n_total, rank * n, (rank + 1) * n)
+    nv, npar, na, nw = MODELS[w["model"]]
+    prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"],
+                       kernels=_rt.KERNEL_FEATURES, work_queue=bool(args.work_queue), block_size=args.block,
+                       min_blocks_per_sm=args.min_blocks)
+    sim = _rt.Sim(prog, device=local)
+    sim.set_solver_params(**w["solver"])
+    sim.set_observer_params(**w["observer_params"])
+    sim.set_tspan(*w["tspan"])
+
+    # host inputs in pinned memory (numpy views of pinned torch tensors)
+    def pinned(a):
+        t = torch.empty(a.size, dtype=torch.float64, pin_memory=True)
+        v = t.numpy()
+        v[:] = a
+        return t, v
+    keep_x0, x0 = pinned(w["x0"])
+    keep_p, pars = pinned(w["pars"])
+    keep_dt, dt0 = pinned(np.full(n, w["solver"]["dt"]))
+    sim.set_problem(x0, pars)
+    sim.seed_rng(1, rank * n, n_total)
+    nfeat = sim.n_features()
+    step_row = {"basic": 5}.get(w["observer"], nfeat - (1 if w["observer"] in ("basicall", "localmax") else 4))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fptr, fbytes, _ = None, None, None
+    gathered = None
+
+    def gather_features():
+        """the one exchange step of the path: features of every shard to rank 0 over NVLink (NCCL)"""
+        nonlocal gathered
+        if not dist:
+            return
+        ptr, nbytes, _ = sim.device_buffer(_rt.BUF_F)
+        local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
+        if rank == 0 and gathered is None:
+            gathered = [torch.empty_like(local_f) for _ in range(world)]
+        dist.gather(local_f, gathered if rank == 0 else None, dst=0)
+
+    def hot_step():
+        sim.set_dt(dt0)          # per-instance dt persists across calls (reference semantics): reset it
+        sim.features(1)          # initializeObserver + features kernels, synchronous
+        ms = sim.last_kernel_ms()
+        gather_features()
+        return ms
+
+    # ---- warm-up, then K timed steps with inputs resident in HBM ------------------------------
+    for _ in range(max(args.warmup, 3)):
+        hot_step()
+    launches0 = sim.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall = time.perf_counter()
+    kernel_ms = [hot_step() for _ in range(args.steps)]
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - launches0
+    steps_per_pass = int(sim.get_steps().astype(np.int64).sum())
+    dev_ms = sum(kernel_ms)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.set_x0(x0)
+        sim.set_pars(pars)
+        sim.set_dt(dt0)
+        sim.features(1)
+        F = sim.get_f()
+        gather_features()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert int(F.reshape(nfeat, n)[step_row].sum()) == steps_per_pass
+    h2d = 8 * n * (nv + npar + 1)
+    d2h = 8 * n * nfeat
+
+    # ---- reduce over ranks -----------------------------------------------------------------------
+    stats = torch.tensor([dev_ms, wall_ms, e2e_s, float(steps_per_pass), float(launches)], dtype=torch.float64, device="cuda")
+    if dist:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms, e2e_s = mx[0].item(), mx[1].item(), mx[2].item()
+        total_steps_per_pass, launches = int(sm[3].item()), int(sm[4].item())
+    else:
+        total_steps_per_pass = steps_per_pass
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    value = total_steps_per_pass * args.steps / (dev_ms * 1e-3)
+    peak_tf, _ = _rt.measure_fp64_peak(local, 5)
+    achieved_tf = w["flops_per_step"] * steps_per_pass * args.steps / (sum(kernel_ms) * 1e-3) / 1e12
+    info = sim.kernel_info(_rt.KERNEL_FEATURES)
+    base, _ = cpu_reference(args.workload, n_total, 1, 1) if not args.no_cpu_baseline else (None, None)
+    line = {
+        "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": value, "unit": "instance-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "instances_per_gpu": n, "accepted_steps_per_pass": total_steps_per_pass,
+                   "l2": "inputs+outputs per pass exceed the 126 MB L2; the kernel is FP64-pipe bound, not memory bound",
+                   "kernel": info, "work_queue": bool(args.work_queue), "wall_ms_per_step": wall_ms / args.steps},
+        "clocks": clocks,
+        "e2e": {"value": total_steps_per_pass * args.steps / e2e_s, "unit": "instance-steps/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "peak_source": "DFMA micro-benchmark measured on this GPU in this run (clode_measure_fp64_peak)",
+                     "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+                     "flops_per_step": w["flops_per_step"]},
+        "cpu_baseline": base,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--npts", type=int, default=0, help="instances per GPU (default 2^20)")
+    ap.add_argument("--work-queue", type=int, default=0)
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--min-blocks", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

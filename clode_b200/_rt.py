@@ -99,6 +99,13 @@ def device_info(device: int = 0) -> DeviceInfoC:
     return info
 
 
+def measure_fp64_peak(device: int = 0, repeats: int = 5) -> tuple[float, float]:
+    """(TFLOP/s, best ms) of a register-resident DFMA micro-benchmark on `device`"""
+    tf, ms = ctypes.c_double(), ctypes.c_double()
+    _check(lib().clode_measure_fp64_peak(device, repeats, ctypes.byref(tf), ctypes.byref(ms)))
+    return tf.value, ms.value
+
+
 @dataclass
 class Program:
     """Description of one JIT-specialised program (clode_program_desc)."""

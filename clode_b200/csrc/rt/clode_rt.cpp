@@ -477,6 +477,76 @@ int clode_device_get_info(int device, clode_device_info *info)
     return CLODE_OK;
 }
 
+int clode_measure_fp64_peak(int device, int repeats, double *tflops, double *ms_best)
+{
+    if (!tflops) return fail(CLODE_ERR_INVALID, "tflops is null");
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (!d) return fail(CLODE_ERR_NO_DRIVER, why);
+    NvrtcApi *rtc = nvrtc(&why);
+    if (!rtc) return fail(CLODE_ERR_NO_DRIVER, why);
+    static const char *src =
+        "extern \"C\" __global__ void __launch_bounds__(256) clode_dfma_peak(double *out, int iters, double a, double b)\n"
+        "{\n"
+        "    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;\n"
+        "    for (int i = 0; i < iters; ++i) {\n"
+        "#pragma unroll\n"
+        "        for (int u = 0; u < 16; ++u) {\n"
+        "            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);\n"
+        "            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);\n"
+        "        }\n"
+        "    }\n"
+        "    out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));\n"
+        "}\n";
+    nvrtcProgram prog;
+    if (rtc->nvrtcCreateProgram(&prog, src, "clode_dfma_peak.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(CLODE_ERR_BUILD, "nvrtcCreateProgram failed");
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-lineinfo"};
+    nvrtcResult nr = rtc->nvrtcCompileProgram(prog, 2, opts);
+    size_t size = 0;
+    if (nr == NVRTC_SUCCESS) nr = rtc->nvrtcGetCUBINSize(prog, &size);
+    std::vector<char> cubin(size);
+    if (nr == NVRTC_SUCCESS) nr = rtc->nvrtcGetCUBIN(prog, cubin.data());
+    rtc->nvrtcDestroyProgram(&prog);
+    if (nr != NVRTC_SUCCESS) return fail(CLODE_ERR_BUILD, "DFMA micro-benchmark failed to compile");
+
+    clode_sim *s = nullptr;
+    int rc = clode_sim_create(device, &s);
+    if (rc) return rc;
+    double best = 1e30;
+    {
+        clode_sim::Scope scope(s);
+        CUmodule mod = nullptr;
+        CUfunction fn = nullptr;
+        CUdeviceptr out = 0;
+        const unsigned block = 256, grid = (unsigned)s->sm_count * 16;
+        int iters = 4096;
+        double a = 0.999999, b = 1e-6;
+        rc = s->cu(d->cuModuleLoadData(&mod, cubin.data()), "cuModuleLoadData");
+        if (!rc) rc = s->cu(d->cuModuleGetFunction(&fn, mod, "clode_dfma_peak"), "clode_dfma_peak");
+        if (!rc) rc = s->cu(d->cuMemAlloc(&out, sizeof(double) * block * grid), "cuMemAlloc");
+        void *params[] = {&out, &iters, &a, &b};
+        for (int r = 0; !rc && r < std::max(repeats, 1) + 1; ++r) { // first launch is a warm-up
+            rc = s->cu(d->cuEventRecord(s->ev0, s->stream), "cuEventRecord");
+            if (!rc) rc = s->cu(d->cuLaunchKernel(fn, grid, 1, 1, block, 1, 1, 0, s->stream, params, nullptr), "clode_dfma_peak");
+            if (!rc) rc = s->cu(d->cuEventRecord(s->ev1, s->stream), "cuEventRecord");
+            if (!rc) rc = s->cu(d->cuStreamSynchronize(s->stream), "clode_dfma_peak");
+            float ms = 0.f;
+            if (!rc) d->cuEventElapsedTime(&ms, s->ev0, s->ev1);
+            if (!rc && r > 0 && ms > 0.f) best = std::min(best, (double)ms);
+        }
+        if (out) d->cuMemFree(out);
+        if (mod) d->cuModuleUnload(mod);
+        if (!rc) {
+            const double flops = (double)grid * block * (double)iters * 16.0 * 8.0 * 2.0;
+            *tflops = flops / (best * 1e-3) / 1e12;
+            if (ms_best) *ms_best = best;
+        }
+    }
+    clode_sim_destroy(s);
+    return rc;
+}
+
 int clode_compile(const clode_program_desc *desc, void **cubin, size_t *cubin_size, char **log)
 {
     ProgramSpec s;

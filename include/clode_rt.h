@@ -62,6 +62,10 @@ typedef struct clode_device_info {
 
 CLODE_API int clode_device_count(int *count);
 CLODE_API int clode_device_get_info(int device, clode_device_info *info);
+/* Roofline denominator for the transient/features kernels: measured FP64 FMA throughput of the
+ * device (register-resident DFMA chains, best of `repeats` launches, CUDA events), in TFLOP/s
+ * counting an FMA as 2 flops.  MEASURED_PEAKS.json has no FP64 entry. */
+CLODE_API int clode_measure_fp64_peak(int device, int repeats, double *tflops, double *ms_best);
 
 /* ---- program: replaces CLODE::setCLbuildOpts / buildProgram / cl::Kernel creation -------
  * (clode/cpp/CLODE.cpp:109-172, clode/cpp/CLODEfeatures.cpp:34-61, clode/cpp/CLODEtrajectory.cpp:25-43).
