@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference(wname: str, n_total: int, steps: int, warmup: int, stride: int = 64):
+def cpu_reference(wname: str, n_total: int, steps: int, warmup: int, stride: int = 4):
     """the reference's own kernels on the host cores (oracle/_ref; falls back to the C port)"""
     from oracle import ref, restate
     from oracle.common import Config, Observer, Solver, seed_states

@@ -122,10 +122,16 @@ CLODE_DEV void store_instance(const Instance &I, const KernelArgs &a, const size
 }
 
 // advance by one ATTEMPT; true when an accepted (or abandoned, flag -1) step completed
-CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const realtype t_end)
+#if !CLODE_ADAPTIVE
+struct Controller {};
+CLODE_DEV Controller make_controller(const SolverParams &) { return Controller(); }
+#endif
+
+CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const Controller &ctl,
+                       const realtype t_end)
 {
 #if CLODE_ADAPTIVE
-    return adaptive_attempt(I, h, clean, sp, t_end);
+    return adaptive_attempt(I, h, clean, sp, ctl, t_end);
 #else
     step_fixed(I);
     return true;
@@ -171,6 +177,7 @@ clode_transient()
 {
     const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
+    const Controller ctl = make_controller(sp);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);
     for (size_t i = work.first(); i < a.n; i = work.next()) {
@@ -180,7 +187,7 @@ clode_transient()
         realtype h = I.dt;
         bool clean = true;
         while (I.t <= t_end && step < sp.max_steps) {
-            if (advance(I, h, clean, sp, t_end))
+            if (advance(I, h, clean, sp, ctl, t_end))
                 ++step;
         }
         store_instance(I, a, i, step);
@@ -194,6 +201,7 @@ clode_initialize_observer()
 {
     const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
+    const Controller ctl = make_controller(sp);
     const ObserverParams op = observer_params(a);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);
@@ -208,7 +216,7 @@ clode_initialize_observer()
             realtype h = I.dt;
             bool clean = true;
             while (I.t < t_end && step < sp.max_steps) { // strict '<' (initializeObserver.cl:62)
-                if (advance(I, h, clean, sp, t_end)) {
+                if (advance(I, h, clean, sp, ctl, t_end)) {
                     ++step;
                     ob.warmup(I, op);
                 }
@@ -233,6 +241,7 @@ clode_features()
 {
     const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
+    const Controller ctl = make_controller(sp);
     const ObserverParams op = observer_params(a);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);
@@ -249,7 +258,7 @@ clode_features()
         bool clean = true;
         bool live = I.t <= t_end && step < sp.max_steps;
         while (live) {
-            if (advance(I, h, clean, sp, t_end)) {
+            if (advance(I, h, clean, sp, ctl, t_end)) {
                 ++step;
                 // features.cl:71-81: update, then event test, then event features
                 ob.update(I, op);
@@ -310,6 +319,7 @@ clode_trajectory()
 {
     const KernelArgs &a = clode_args;
     const SolverParams sp = solver_params(a);
+    const Controller ctl = make_controller(sp);
     const realtype t_end = (realtype)a.t1;
     WorkSource work = work_source(a);
     for (size_t i = work.first(); i < a.n; i = work.next()) {
@@ -321,7 +331,7 @@ clode_trajectory()
         realtype h = I.dt;
         bool clean = true;
         while (I.t <= t_end && step < sp.max_steps && row < sp.max_store) {
-            if (advance(I, h, clean, sp, t_end)) {
+            if (advance(I, h, clean, sp, ctl, t_end)) {
                 ++step;
                 if (step % sp.nout == 0) {
                     ++row;

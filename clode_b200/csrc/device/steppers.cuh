@@ -195,14 +195,86 @@ CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, re
 }
 #endif
 
+// 0.8 * (reltol/err)^(1/(order+1)) for the step-size controller (adaptive_explicit_step.clh:51,66).
+// Bit-exact tier, reference-math builds and single precision evaluate it as written, with pow().
+// Production double: libdevice's pow() costs ~100 FP64-pipe instructions on a ~40-deep dependent
+// chain, plus an IEEE division for its argument — a third of a Lorenz dopri5 step — for a factor
+// that is immediately clamped to [MAX_SHRINK, 5].  There the factor is computed division-free as
+//     0.8 * reltol^(1/(p+1)) * err^(-1/(p+1)),
+// the first two terms once per kernel, the last by Newton's iteration on z^-(p+1) = err seeded from
+// the SFU (FP32 lg2/ex2): ~14 FP64 instructions, <= 4 ulp, well inside OpenCL C's 16-ulp bound
+// for pow.  err outside [1e-30, 1e30] saturates, which the clamps make indistinguishable.
+struct Controller {
+    realtype reltol, floor_;
+    realtype scale; // 0.8 * reltol^(1/(p+1))   (production double only)
+};
+#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH)
+#define CLODE_EXACT_CONTROLLER 1
+CLODE_DEV realtype controller_factor(const Controller &c, realtype nerr)
+{
+    return RCONST(0.8) * pow(c.reltol / nerr, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
+}
+#else
+#define CLODE_EXACT_CONTROLLER 0
+CLODE_DEV double controller_factor(const Controller &c, double nerr)
+{
+    const double x = fmin(fmax(nerr, 1e-30), 1e30);
+#if defined(EXPLICIT_BS23)
+    return c.scale * rcbrt(x);
+#else
+    double z = (double)exp2f(-0.2f * __log2f((float)x)); // ~ x^(-1/5), relative error ~1e-6
+    const double fifth_x = -0.2 * x;
+    // Newton on f(z) = z^-5 - x :  z <- z (1.2 - 0.2 x z^5), twice: 1e-6 -> 1e-11 -> rounding level
+    double z2 = z * z;
+    z = z * fma(fifth_x, z2 * z2 * z, 1.2);
+    z2 = z * z;
+    z = z * fma(fifth_x, z2 * z2 * z, 1.2);
+    return c.scale * z;
+#endif
+}
+#endif
+
+CLODE_DEV Controller make_controller(const SolverParams &sp)
+{
+    Controller c;
+    c.reltol = sp.reltol;
+    c.floor_ = sp.abstol / sp.reltol;
+    c.scale = RCONST(0.8) * pow(sp.reltol, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
+    return c;
+}
+
+// hmin = 16 * | |nextafter(t, 1.1 t_end)| - t |   (adaptive_explicit_step.clh:17; "16 eps(t)")
+// nextafter written out on the bit pattern: same result as the library call for every non-NaN
+// input, without its NaN / signalling paths (about a third of the instructions).
+CLODE_DEV realtype step_floor(const realtype t, const realtype t_end)
+{
+#if defined(CLODE_SINGLE_PRECISION)
+    return RCONST(16.0) * fabs(fabs(nextafter(t, RCONST(1.1) * t_end)) - t);
+#else
+    const double target = 1.1 * t_end;
+    long long bits = __double_as_longlong(t);
+    double next;
+    if (t == target || target != target)
+        next = (target != target) ? target : t; // equal: unchanged; NaN target propagates
+    else if (t == 0.0)
+        next = __longlong_as_double(target > 0.0 ? 1LL : (long long)0x8000000000000001ULL); // smallest subnormal toward target
+    else {
+        bits += ((t < target) == (t > 0.0)) ? 1LL : -1LL; // away from zero when moving outward, else toward it
+        next = __longlong_as_double(bits);
+    }
+    return 16.0 * fabs(fabs(next) - t);
+#endif
+}
+
 // One attempt of the step-size controller, adaptive_explicit_step.clh:9-81.
 // `h` is the trial step carried between attempts, `clean` is the reference's
 // noFailedSteps.  Returns true when the reference's stepper() would have returned
 // (step accepted, or abandoned at hmin with its -1 flag); false = try again.
-CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const realtype t_end)
+CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const Controller &ctl,
+                                 const realtype t_end)
 {
-    const realtype floor_ = sp.abstol / sp.reltol;
-    const realtype hmin = RCONST(16.0) * fabs(fabs(nextafter(I.t, RCONST(1.1) * t_end)) - I.t);
+    const realtype floor_ = ctl.floor_;
+    const realtype hmin = step_floor(I.t, t_end);
     realtype t1, xn[NV], kn[NV], err[NV];
 
     h = clamp(h, hmin, sp.dtmax);
@@ -223,7 +295,7 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     }
     realtype factor = RCONST(0.5);
     if (clean)
-        factor = RCONST(0.8) * pow(sp.reltol / nerr, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
+        factor = controller_factor(ctl, nerr);
     if (reject) {
         h *= clean ? fmax(MAX_SHRINK, factor) : RCONST(0.5);
         clean = false;

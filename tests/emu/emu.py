@@ -58,6 +58,8 @@ class EmuLib:
         ]
         if cfg.math == "pm":
             defs.append("-DCLODE_BITEXACT")
+        else:
+            defs.append("-DCLODE_REFERENCE_MATH")  # libm flavour: no performance substitutions (controller root)
         h = hashlib.sha1(" ".join(defs).encode())
         for f in sorted(os.listdir(DEVICE)) + ["../../../tests/emu/cuda_emu.h", "../../../tests/emu/emu_driver.cpp"]:
             h.update(open(os.path.join(DEVICE, f), "rb").read())
