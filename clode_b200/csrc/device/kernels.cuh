@@ -19,10 +19,10 @@
 #define CLODE_KERNELS_CUH
 
 #ifndef CLODE_BLOCK
-#define CLODE_BLOCK 64
+#define CLODE_BLOCK 128
 #endif
 #ifndef CLODE_MIN_BLOCKS
-#define CLODE_MIN_BLOCKS 1
+#define CLODE_MIN_BLOCKS 4
 #endif
 
 // Launch arguments: one struct in __constant__ memory (`clode_args`), written by the host

@@ -40,8 +40,8 @@ struct Tri {
     __device__ __forceinline__ void reset() { hi = -BIG_REAL; lo = BIG_REAL; mean = ZERO; }
     __device__ __forceinline__ void push(realtype v, unsigned int count)
     {
-        hi = fmax(v, hi);
-        lo = fmin(v, lo);
+        hi = max_nn(v, hi);
+        lo = min_nn(v, lo);
         runningMean(&mean, v, count);
     }
     template <class V> __device__ __forceinline__ void visit(V &v) { v(hi); v(lo); v(mean); }
@@ -85,16 +85,16 @@ struct Extents {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            xmax[j] = fmax(I.x[j], xmax[j]);
-            xmin[j] = fmin(I.x[j], xmin[j]);
+            xmax[j] = max_nn(I.x[j], xmax[j]);
+            xmin[j] = min_nn(I.x[j], xmin[j]);
             xmean[j] = runningMeanTime(xmean[j], I.x[j], dt, span);
-            dxmax[j] = fmax(I.k1[j], dxmax[j]);
-            dxmin[j] = fmin(I.k1[j], dxmin[j]);
+            dxmax[j] = max_nn(I.k1[j], dxmax[j]);
+            dxmin[j] = min_nn(I.k1[j], dxmin[j]);
         }
 #pragma unroll
         for (int j = 0; j < N_AUX; ++j) {
-            amax[j] = fmax(I.aux[j], amax[j]);
-            amin[j] = fmin(I.aux[j], amin[j]);
+            amax[j] = max_nn(I.aux[j], amax[j]);
+            amin[j] = min_nn(I.aux[j], amin[j]);
             amean[j] = runningMeanTime(amean[j], I.aux[j], dt, span);
         }
     }
@@ -103,16 +103,16 @@ struct Extents {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            xmax[j] = fmax(I.x[j], xmax[j]);
-            xmin[j] = fmin(I.x[j], xmin[j]);
+            xmax[j] = max_nn(I.x[j], xmax[j]);
+            xmin[j] = min_nn(I.x[j], xmin[j]);
             runningMean(&xmean[j], I.x[j], count);
-            dxmax[j] = fmax(I.k1[j], dxmax[j]);
-            dxmin[j] = fmin(I.k1[j], dxmin[j]);
+            dxmax[j] = max_nn(I.k1[j], dxmax[j]);
+            dxmin[j] = min_nn(I.k1[j], dxmin[j]);
         }
 #pragma unroll
         for (int j = 0; j < N_AUX; ++j) {
-            amax[j] = fmax(I.aux[j], amax[j]);
-            amin[j] = fmin(I.aux[j], amin[j]);
+            amax[j] = max_nn(I.aux[j], amax[j]);
+            amin[j] = min_nn(I.aux[j], amin[j]);
             runningMean(&amean[j], I.aux[j], count);
         }
     }
@@ -163,11 +163,11 @@ struct Observer {
         const realtype dt = I.t - t_last;
         t_last = I.t;
         const realtype span = I.t - t_start;
-        xmax = fmax(I.x[F_VAR_IX], xmax);
-        xmin = fmin(I.x[F_VAR_IX], xmin);
+        xmax = max_nn(I.x[F_VAR_IX], xmax);
+        xmin = min_nn(I.x[F_VAR_IX], xmin);
         xmean = runningMeanTime(xmean, I.x[F_VAR_IX], dt, span);
-        dxmax = fmax(I.k1[F_VAR_IX], dxmax);
-        dxmin = fmin(I.k1[F_VAR_IX], dxmin);
+        dxmax = max_nn(I.k1[F_VAR_IX], dxmax);
+        dxmin = min_nn(I.k1[F_VAR_IX], dxmin);
     }
     __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
@@ -469,8 +469,8 @@ struct Observer {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            ext.xmax[j] = fmax(I.x[j], ext.xmax[j]);
-            ext.xmin[j] = fmin(I.x[j], ext.xmin[j]);
+            ext.xmax[j] = max_nn(I.x[j], ext.xmax[j]);
+            ext.xmin[j] = min_nn(I.x[j], ext.xmin[j]);
         }
     }
     __device__ __forceinline__ void arm(const Instance &, const ObserverParams &op)
@@ -597,10 +597,10 @@ struct Observer {
     }
     __device__ __forceinline__ void warmup(const Instance &I, const ObserverParams &)
     {
-        g_xmax = fmax(g_xmax, I.x[E_VAR_IX]);
-        g_xmin = fmin(g_xmin, I.x[E_VAR_IX]);
-        g_dxmax = fmax(g_dxmax, I.k1[E_VAR_IX]);
-        g_dxmin = fmin(g_dxmin, I.k1[E_VAR_IX]);
+        g_xmax = max_nn(I.x[E_VAR_IX], g_xmax);
+        g_xmin = min_nn(I.x[E_VAR_IX], g_xmin);
+        g_dxmax = max_nn(I.k1[E_VAR_IX], g_dxmax);
+        g_dxmin = min_nn(I.k1[E_VAR_IX], g_dxmin);
     }
     __device__ __forceinline__ void arm(const Instance &I, const ObserverParams &op)
     {

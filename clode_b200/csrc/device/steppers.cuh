@@ -38,6 +38,15 @@ struct SolverParams {
     unsigned int max_steps, max_store, nout;
 };
 
+// fmax/fmin where the SECOND operand is known not to be NaN (a running extreme that started finite, a
+// solver parameter, ...).  Same value as fmax(v, m) / fmin(v, m) for every input — a NaN v yields m —
+// except possibly the sign of a zero result.  In SASS the library fmax on doubles is DSETP + FSEL +
+// SEL + LOP3 + moves (~7 issue slots, NaN quieting included); this form is DSETP + 2 SEL.  The step loop
+// evaluates ~20 of them per attempt.
+CLODE_DEV realtype max_nn(const realtype v, const realtype m) { return v > m ? v : m; }
+CLODE_DEV realtype min_nn(const realtype v, const realtype m) { return v < m ? v : m; }
+CLODE_DEV realtype clamp_nn(const realtype v, const realtype lo, const realtype hi) { return min_nn(max_nn(v, lo), hi); }
+
 // user right-hand side; the definition is appended after all engine code (clode/cpp/steppers.cl:50)
 __device__ __forceinline__ void getRHS(const realtype t, const realtype x_[], const realtype p_[],
                                        realtype dx_[], realtype aux_[], const realtype w_[]);
@@ -119,78 +128,94 @@ CLODE_DEV void step_fixed(Instance &I)
 #if defined(EXPLICIT_BS23)
 #define ERR_ORDER RCONST(2.0)
 #define MAX_SHRINK RCONST(0.5)
+// Tableau in the constant bank: each coefficient is then a c[bank][offset] operand of the DFMA/DMUL
+// that uses it.  As literals the compiler re-materialises every 64-bit constant with two UMOVs per
+// use inside the attempt loop (12 % of all issued instructions in the first profile).  Values are the
+// reference's own quotient expressions, folded at compile time (adaptive_bs23.clh:9-25).
+__constant__ realtype clode_tab[9] = {
+    RCONST(0.5), RCONST(0.75),
+    RCONST(2.0) / RCONST(9.0), RCONST(1.0) / RCONST(3.0), RCONST(4.0) / RCONST(9.0),
+    RCONST(-5.0) / RCONST(72.0), RCONST(1.0) / RCONST(12.0), RCONST(1.0) / RCONST(9.0), RCONST(-1.0) / RCONST(8.0)};
 // Bogacki-Shampine 3(2), adaptive_bs23.clh:27-63.  Returns the effective step.
 CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, realtype xn[NV],
                               realtype kn[NV], realtype err[NV])
 {
+    const realtype *c = clode_tab;
     t1 = I.t + h_in;
     const realtype h = t1 - I.t;
     realtype y[NV], k2[NV], k3[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * RCONST(0.5) * I.k1[j];
-    getRHS(I.t + h * RCONST(0.5), y, I.p, k2, I.aux, I.w);
+        y[j] = I.x[j] + h * c[0] * I.k1[j];
+    getRHS(I.t + h * c[0], y, I.p, k2, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * RCONST(0.75) * k2[j];
-    getRHS(I.t + h * RCONST(0.75), y, I.p, k3, I.aux, I.w);
+        y[j] = I.x[j] + h * c[1] * k2[j];
+    getRHS(I.t + h * c[1], y, I.p, k3, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        xn[j] = I.x[j] + h * (RCONST(2.0) / RCONST(9.0) * I.k1[j] + RCONST(1.0) / RCONST(3.0) * k2[j] +
-                              RCONST(4.0) / RCONST(9.0) * k3[j]);
+        xn[j] = I.x[j] + h * (c[2] * I.k1[j] + c[3] * k2[j] + c[4] * k3[j]);
     getRHS(t1, xn, I.p, kn, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        err[j] = h * (RCONST(-5.0) / RCONST(72.0) * I.k1[j] + RCONST(1.0) / RCONST(12.0) * k2[j] +
-                      RCONST(1.0) / RCONST(9.0) * k3[j] + RCONST(-1.0) / RCONST(8.0) * kn[j]);
+        err[j] = h * (c[5] * I.k1[j] + c[6] * k2[j] + c[7] * k3[j] + c[8] * kn[j]);
     return h;
 }
 #else // EXPLICIT_DOPRI5
 #define ERR_ORDER RCONST(4.0)
 #define MAX_SHRINK RCONST(0.1)
+// Tableau in the constant bank (see the note at the bs23 table); adaptive_dp45.clh:10-56.
+enum { A2, A3, A4, A5, B21, B31, B32, B41, B42, B43, B51, B52, B53, B54, B61, B62, B63, B64, B65,
+       C1, C3, C4, C5, C6, E1, E3, E4, E5, E6, E7, DP_TAB_SIZE };
+__constant__ realtype clode_tab[DP_TAB_SIZE] = {
+    RCONST(1.0) / RCONST(5.0), RCONST(3.0) / RCONST(10.0), RCONST(4.0) / RCONST(5.0), RCONST(8.0) / RCONST(9.0),
+    RCONST(1.0) / RCONST(5.0),
+    RCONST(3.0) / RCONST(40.0), RCONST(9.0) / RCONST(40.0),
+    RCONST(44.0) / RCONST(45.0), RCONST(-56.0) / RCONST(15.0), RCONST(32.0) / RCONST(9.0),
+    RCONST(19372.0) / RCONST(6561.0), RCONST(-25360.0) / RCONST(2187.0), RCONST(64448.0) / RCONST(6561.0),
+    RCONST(-212.0) / RCONST(729.0),
+    RCONST(9017.0) / RCONST(3168.0), RCONST(-355.0) / RCONST(33.0), RCONST(46732.0) / RCONST(5247.0),
+    RCONST(49.0) / RCONST(176.0), RCONST(-5103.0) / RCONST(18656.0),
+    RCONST(35.0) / RCONST(384.0), RCONST(500.0) / RCONST(1113.0), RCONST(125.0) / RCONST(192.0),
+    RCONST(-2187.0) / RCONST(6784.0), RCONST(11.0) / RCONST(84.0),
+    RCONST(71.0) / RCONST(57600.0), RCONST(-71.0) / RCONST(16695.0), RCONST(71.0) / RCONST(1920.0),
+    RCONST(-17253.0) / RCONST(339200.0), RCONST(22.0) / RCONST(525.0), RCONST(-1.0) / RCONST(40.0)};
 // Dormand-Prince 5(4), adaptive_dp45.clh:58-110.  Returns the effective step.
 CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, realtype xn[NV],
                               realtype kn[NV], realtype err[NV])
 {
+    const realtype *c = clode_tab;
     t1 = I.t + h_in;
     const realtype h = t1 - I.t;
     realtype y[NV], k2[NV], k3[NV], k4[NV], k5[NV], k6[NV];
     const realtype *k1 = I.k1;
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * (RCONST(1.0) / RCONST(5.0) * k1[j]);
-    getRHS(I.t + RCONST(1.0) / RCONST(5.0) * h, y, I.p, k2, I.aux, I.w);
+        y[j] = I.x[j] + h * (c[B21] * k1[j]);
+    getRHS(I.t + c[A2] * h, y, I.p, k2, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * (RCONST(3.0) / RCONST(40.0) * k1[j] + RCONST(9.0) / RCONST(40.0) * k2[j]);
-    getRHS(I.t + RCONST(3.0) / RCONST(10.0) * h, y, I.p, k3, I.aux, I.w);
+        y[j] = I.x[j] + h * (c[B31] * k1[j] + c[B32] * k2[j]);
+    getRHS(I.t + c[A3] * h, y, I.p, k3, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * (RCONST(44.0) / RCONST(45.0) * k1[j] + RCONST(-56.0) / RCONST(15.0) * k2[j] +
-                             RCONST(32.0) / RCONST(9.0) * k3[j]);
-    getRHS(I.t + RCONST(4.0) / RCONST(5.0) * h, y, I.p, k4, I.aux, I.w);
+        y[j] = I.x[j] + h * (c[B41] * k1[j] + c[B42] * k2[j] + c[B43] * k3[j]);
+    getRHS(I.t + c[A4] * h, y, I.p, k4, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * (RCONST(19372.0) / RCONST(6561.0) * k1[j] + RCONST(-25360.0) / RCONST(2187.0) * k2[j] +
-                             RCONST(64448.0) / RCONST(6561.0) * k3[j] + RCONST(-212.0) / RCONST(729.0) * k4[j]);
-    getRHS(I.t + RCONST(8.0) / RCONST(9.0) * h, y, I.p, k5, I.aux, I.w);
+        y[j] = I.x[j] + h * (c[B51] * k1[j] + c[B52] * k2[j] + c[B53] * k3[j] + c[B54] * k4[j]);
+    getRHS(I.t + c[A5] * h, y, I.p, k5, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        y[j] = I.x[j] + h * (RCONST(9017.0) / RCONST(3168.0) * k1[j] + RCONST(-355.0) / RCONST(33.0) * k2[j] +
-                             RCONST(46732.0) / RCONST(5247.0) * k3[j] + RCONST(49.0) / RCONST(176.0) * k4[j] +
-                             RCONST(-5103.0) / RCONST(18656.0) * k5[j]);
+        y[j] = I.x[j] + h * (c[B61] * k1[j] + c[B62] * k2[j] + c[B63] * k3[j] + c[B64] * k4[j] + c[B65] * k5[j]);
     getRHS(I.t + h, y, I.p, k6, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        xn[j] = I.x[j] + h * (RCONST(35.0) / RCONST(384.0) * k1[j] + RCONST(500.0) / RCONST(1113.0) * k3[j] +
-                              RCONST(125.0) / RCONST(192.0) * k4[j] + RCONST(-2187.0) / RCONST(6784.0) * k5[j] +
-                              RCONST(11.0) / RCONST(84.0) * k6[j]);
+        xn[j] = I.x[j] + h * (c[C1] * k1[j] + c[C3] * k3[j] + c[C4] * k4[j] + c[C5] * k5[j] + c[C6] * k6[j]);
     getRHS(t1, xn, I.p, kn, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        err[j] = h * (RCONST(71.0) / RCONST(57600.0) * k1[j] + RCONST(-71.0) / RCONST(16695.0) * k3[j] +
-                      RCONST(71.0) / RCONST(1920.0) * k4[j] + RCONST(-17253.0) / RCONST(339200.0) * k5[j] +
-                      RCONST(22.0) / RCONST(525.0) * k6[j] + RCONST(-1.0) / RCONST(40.0) * kn[j]);
+        err[j] = h * (c[E1] * k1[j] + c[E3] * k3[j] + c[E4] * k4[j] + c[E5] * k5[j] + c[E6] * k6[j] + c[E7] * kn[j]);
     return h;
 }
 #endif
@@ -277,14 +302,15 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     const realtype hmin = step_floor(I.t, t_end);
     realtype t1, xn[NV], kn[NV], err[NV];
 
-    h = clamp(h, hmin, sp.dtmax);
+    h = clamp_nn(h, hmin, sp.dtmax);
     h = trial_step(I, h, t1, xn, kn, err);
 
     realtype nerr = ZERO;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        err[j] /= fmax(fmax(fabs(I.x[j]), fabs(xn[j])), floor_);
-        nerr = fmax(fabs(err[j]), nerr);
+        // fmax(fmax(|x|, |xn|), floor) and norm_inf's fmax(|e|, running), NaN operands ignored as in the reference
+        err[j] /= max_nn(fabs(I.x[j]), max_nn(fabs(xn[j]), floor_));
+        nerr = max_nn(fabs(err[j]), nerr);
     }
     const bool reject = nerr > sp.reltol;
     if (reject && h <= hmin) { // cannot shrink further: stepper() returns -1, state untouched
@@ -297,14 +323,14 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     if (clean)
         factor = controller_factor(ctl, nerr);
     if (reject) {
-        h *= clean ? fmax(MAX_SHRINK, factor) : RCONST(0.5);
+        h *= clean ? max_nn(factor, MAX_SHRINK) : RCONST(0.5);
         clean = false;
         return false;
     }
     if (clean)
-        h *= fmin(RCONST(5.0), factor);
-    h = fmin(h, t_end - t1);
-    h = clamp(h, hmin, sp.dtmax);
+        h *= min_nn(factor, RCONST(5.0));
+    h = min_nn(t_end - t1, h); // fmin(h, t_end - t1): h is never NaN here
+    h = clamp_nn(h, hmin, sp.dtmax);
     I.dt = h;
     I.t = t1;
 #pragma unroll

@@ -78,7 +78,7 @@ struct ProgramSpec {
     int f_var = 0, e_var = 0, n_store = 0;
     int kernels = CLODE_KERNEL_TRANSIENT;
     bool bit_exact = false, work_queue = false;
-    int block = 64, min_blocks = 1;
+    int block = 128, min_blocks = 4;
 };
 
 int parse_desc(const clode_program_desc *d, ProgramSpec &s)
@@ -101,9 +101,9 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.bit_exact = d->bit_exact != 0;
     if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
     s.work_queue = d->work_queue != 0;
-    s.block = d->block_size > 0 ? d->block_size : 64;
+    s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
-    s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 1;
+    s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4;
     return CLODE_OK;
 }
 
