@@ -1,0 +1,31 @@
+"""clode_b200 — B200-native ensemble ODE engine behind the clODE API.
+
+The Python-visible names are those of the reference package (clode/__init__.py:87-168) for the hot
+path: `Simulator`, `FeatureSimulator`, `TrajectorySimulator`, `Stepper`, `Observer`, `ObserverOutput`,
+`TrajectoryOutput`, the parameter structs and the runtime helpers.  Importing the front end needs the
+compiled extension (`python -m clode_b200.build`); the low-level ctypes binding `clode_b200._rt` and
+the build helpers import without it.
+"""
+__version__ = "0.1.0"
+
+_FRONT_END = ["CLDeviceType", "CLVendor", "DeviceInfo", "PlatformInfo", "OpenCLResource", "initialize_runtime",
+              "print_opencl", "query_opencl", "LogLevel", "get_log_level", "set_log_level", "set_log_pattern",
+              "ProblemInfo", "SolverParams", "Stepper", "Simulator", "FeatureSimulator", "Observer", "ObserverParams",
+              "ObserverOutput", "TrajectorySimulator", "TrajectoryOutput"]
+__all__ = list(_FRONT_END)
+
+
+def __getattr__(name):
+    # lazy: `import clode_b200` must work before the extension is built (build.py lives in this package)
+    if name in _FRONT_END:
+        from . import features, runtime, solver, trajectory
+        from .cpp import clode_cpp_wrapper as w
+
+        table = {"ProblemInfo": w.ProblemInfo, "SolverParams": w.SolverParams, "ObserverParams": w.ObserverParams,
+                 "Stepper": solver.Stepper, "Simulator": solver.Simulator, "FeatureSimulator": features.FeatureSimulator,
+                 "Observer": features.Observer, "ObserverOutput": features.ObserverOutput,
+                 "TrajectorySimulator": trajectory.TrajectorySimulator, "TrajectoryOutput": trajectory.TrajectoryOutput}
+        if name in table:
+            return table[name]
+        return getattr(runtime, name)
+    raise AttributeError(name)

@@ -34,6 +34,18 @@ struct ObserverParams {
 
 // ---- small building blocks -----------------------------------------------------------
 
+// engine-internal forms of runningMeanTime / runningMean (clODE_utilities.cl:167-177) whose division
+// goes through div_nr (IEEE in the reference-arithmetic builds, Newton reciprocal in production)
+CLODE_DEV realtype mean_time(realtype mean, realtype v, realtype dt, realtype span)
+{
+    return mean + div_nr((v - mean) * dt, span);
+}
+CLODE_DEV void mean_count(realtype *mean, realtype v, unsigned int count)
+{
+    if (count == 1) *mean = v;
+    else if (count > 1) *mean += div_nr(v - *mean, (realtype)count);
+}
+
 // (max, min, running mean) accumulator used for every per-event statistic
 struct Tri {
     realtype hi, lo, mean;
@@ -42,7 +54,7 @@ struct Tri {
     {
         hi = max_nn(v, hi);
         lo = min_nn(v, lo);
-        runningMean(&mean, v, count);
+        mean_count(&mean, v, count);
     }
     template <class V> __device__ __forceinline__ void visit(V &v) { v(hi); v(lo); v(mean); }
 };
@@ -87,7 +99,7 @@ struct Extents {
         for (int j = 0; j < NV; ++j) {
             xmax[j] = max_nn(I.x[j], xmax[j]);
             xmin[j] = min_nn(I.x[j], xmin[j]);
-            xmean[j] = runningMeanTime(xmean[j], I.x[j], dt, span);
+            xmean[j] = mean_time(xmean[j], I.x[j], dt, span);
             dxmax[j] = max_nn(I.k1[j], dxmax[j]);
             dxmin[j] = min_nn(I.k1[j], dxmin[j]);
         }
@@ -95,7 +107,7 @@ struct Extents {
         for (int j = 0; j < N_AUX; ++j) {
             amax[j] = max_nn(I.aux[j], amax[j]);
             amin[j] = min_nn(I.aux[j], amin[j]);
-            amean[j] = runningMeanTime(amean[j], I.aux[j], dt, span);
+            amean[j] = mean_time(amean[j], I.aux[j], dt, span);
         }
     }
     // per-step means (nhood1: observer_neighborhood_1.clh:250-261)
@@ -105,7 +117,7 @@ struct Extents {
         for (int j = 0; j < NV; ++j) {
             xmax[j] = max_nn(I.x[j], xmax[j]);
             xmin[j] = min_nn(I.x[j], xmin[j]);
-            runningMean(&xmean[j], I.x[j], count);
+            mean_count(&xmean[j], I.x[j], count);
             dxmax[j] = max_nn(I.k1[j], dxmax[j]);
             dxmin[j] = min_nn(I.k1[j], dxmin[j]);
         }
@@ -113,7 +125,7 @@ struct Extents {
         for (int j = 0; j < N_AUX; ++j) {
             amax[j] = max_nn(I.aux[j], amax[j]);
             amin[j] = min_nn(I.aux[j], amin[j]);
-            runningMean(&amean[j], I.aux[j], count);
+            mean_count(&amean[j], I.aux[j], count);
         }
     }
     template <class V> __device__ __forceinline__ void visit(V &v)
@@ -165,7 +177,7 @@ struct Observer {
         const realtype span = I.t - t_start;
         xmax = max_nn(I.x[F_VAR_IX], xmax);
         xmin = min_nn(I.x[F_VAR_IX], xmin);
-        xmean = runningMeanTime(xmean, I.x[F_VAR_IX], dt, span);
+        xmean = mean_time(xmean, I.x[F_VAR_IX], dt, span);
         dxmax = max_nn(I.k1[F_VAR_IX], dxmax);
         dxmin = min_nn(I.k1[F_VAR_IX], dxmin);
     }
@@ -634,7 +646,7 @@ struct Observer {
                 }
             } else {
                 const realtype since = I.t - t_this_down;
-                if (since > 0.0) down_mean = runningMeanTime(down_mean, I.x[F_VAR_IX], dt, since);
+                if (since > 0.0) down_mean = mean_time(down_mean, I.x[F_VAR_IX], dt, since);
             }
         }
     }

@@ -47,6 +47,25 @@ CLODE_DEV realtype max_nn(const realtype v, const realtype m) { return v > m ? v
 CLODE_DEV realtype min_nn(const realtype v, const realtype m) { return v < m ? v : m; }
 CLODE_DEV realtype clamp_nn(const realtype v, const realtype lo, const realtype hi) { return min_nn(max_nn(v, lo), hi); }
 
+// a / b for the engine's own bookkeeping divisions (error normalisation, running means).
+// Reference-arithmetic builds: the IEEE division, as written in the reference.  Production double:
+// reciprocal by MUFU.RCP64H + two Newton steps, then one multiply — <= 2 ulp, no denormal / overflow
+// slow path (the divisors here are max(|x|, abstol/reltol) and elapsed times: normal, finite numbers).
+// libdevice's correctly-rounded division costs 8 FP64 + ~6 control instructions per call and a Lorenz
+// dopri5 attempt makes four of them.  The user's RHS keeps the IEEE `/`.
+#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH) || defined(__CUDACC_EMU__)
+CLODE_DEV realtype div_nr(const realtype a, const realtype b) { return a / b; }
+#else
+CLODE_DEV double div_nr(const double a, const double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    r = fma(r, fma(-b, r, 1.0), r);
+    return a * r;
+}
+#endif
+
 // user right-hand side; the definition is appended after all engine code (clode/cpp/steppers.cl:50)
 __device__ __forceinline__ void getRHS(const realtype t, const realtype x_[], const realtype p_[],
                                        realtype dx_[], realtype aux_[], const realtype w_[]);
@@ -309,7 +328,7 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         // fmax(fmax(|x|, |xn|), floor) and norm_inf's fmax(|e|, running), NaN operands ignored as in the reference
-        err[j] /= max_nn(fabs(I.x[j]), max_nn(fabs(xn[j]), floor_));
+        err[j] = div_nr(err[j], max_nn(fabs(I.x[j]), max_nn(fabs(xn[j]), floor_)));
         nerr = max_nn(fabs(err[j]), nerr);
     }
     const bool reject = nerr > sp.reltol;

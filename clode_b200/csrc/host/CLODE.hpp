@@ -1,0 +1,142 @@
+// CLODE — host class of the clODE C++ API (clode/cpp/CLODE.hpp:22-189), re-implemented on the
+// B200 runtime (include/clode_rt.h).  Public names, signatures and semantics are the reference's;
+// what changed is underneath: no cl::Buffer / cl::Kernel members, but one runtime simulation
+// object per selected GPU, each holding a contiguous shard of the ensemble.
+#pragma once
+
+#include "OpenCLResource.hpp"
+#include "clODE_struct_defs.hpp"
+#include "clode_rt.h"
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+struct ProblemInfo {
+    std::string clRHSfilename;
+    cl_int nVar = 0, nPar = 0, nAux = 0, nWiener = 0;
+    std::vector<std::string> varNames, parNames, auxNames;
+
+    ProblemInfo(std::string clRHSfilename, cl_int nVar, cl_int nPar, cl_int nAux, cl_int nWiener,
+                std::vector<std::string> varNames, std::vector<std::string> parNames, std::vector<std::string> auxNames)
+        : clRHSfilename(clRHSfilename), nVar(nVar), nPar(nPar), nAux(nAux), nWiener(nWiener), varNames(varNames),
+          parNames(parNames), auxNames(auxNames)
+    {
+    }
+    ProblemInfo(std::string clRHSfilename, std::vector<std::string> varNames, std::vector<std::string> parNames,
+                std::vector<std::string> auxNames = std::vector<std::string>(), cl_int nWiener = 0)
+        : clRHSfilename(clRHSfilename), nVar((cl_int)varNames.size()), nPar((cl_int)parNames.size()),
+          nAux((cl_int)auxNames.size()), nWiener(nWiener), varNames(varNames), parNames(parNames), auxNames(auxNames)
+    {
+    }
+    ProblemInfo() {}
+
+    void setVarNames(std::vector<std::string> v) { varNames = v; nVar = (cl_int)v.size(); }
+    void setParNames(std::vector<std::string> v) { parNames = v; nPar = (cl_int)v.size(); }
+    void setAuxNames(std::vector<std::string> v) { auxNames = v; nAux = (cl_int)v.size(); }
+    std::vector<std::string> getVarNames() { return varNames; }
+    std::vector<std::string> getParNames() { return parNames; }
+    std::vector<std::string> getAuxNames() { return auxNames; }
+};
+
+class CLODE
+{
+protected:
+    ProblemInfo prob;
+    std::string clRHSfilename;
+    cl_int nVar = 0, nPar = 0, nAux = 0, nWiener = 0;
+    cl_int nPts = 0;
+
+    std::string stepper;
+    std::vector<std::string> availableSteppers;
+    std::map<std::string, std::string> stepperDefineMap;
+
+    bool clSinglePrecision = false;
+    size_t realSize = 8;
+
+    OpenCLResource opencl;
+    std::string clodeRoot;
+
+    cl_int nRNGstate = 2;
+
+    SolverParams<cl_double> sp{0.1, 0.5, 1e-6, 1e-3, 1000000u, 1000000u, 1u};
+    std::vector<cl_double> tspan{0.0, 1.0}, x0, pars, xf, dt, tf;
+    size_t x0elements = 0, parselements = 0, RNGelements = 0;
+    std::vector<cl_ulong> RNGstate;
+
+    std::string clprogramstring, buildOptions, ODEsystemsource;
+
+    // ---- runtime objects: one per GPU, each owning instances [offset, offset + count) ----
+    struct Shard {
+        clode_sim *sim = nullptr;
+        int device = 0;
+        size_t offset = 0, count = 0;
+    };
+    struct Runtime; // owns the clode_sim handles; shared so that copies of a CLODE stay valid
+    std::shared_ptr<Runtime> runtime;
+    std::vector<Shard> &shards();
+    bool programBuilt = false;
+
+    // what the derived class needs compiled into the program
+    virtual int kernelMask() const { return CLODE_KERNEL_TRANSIENT; }
+    virtual void fillProgramDesc(clode_program_desc &) const {}
+    virtual void onNptsChanged() {}
+
+    void check(int status, const char *where) const; // log + throw on a runtime error
+    void makeShards();
+    void buildProgram();
+    void pushSolverParams();
+    void setNpts(cl_int newNpts);
+    void uploadRows(const std::vector<cl_double> &full, int rows, int (*setter)(clode_sim *, const double *, size_t),
+                    const char *where);
+    void downloadRows(std::vector<cl_double> &full, int rows, int which, const char *where);
+    void runOnShards(int kernel, int initialize, const char *where);
+    std::string getStepperDefine();
+
+public:
+    CLODE(ProblemInfo prob, std::string stepper, bool clSinglePrecision, OpenCLResource opencl, const std::string clodeRoot);
+    CLODE(ProblemInfo prob, std::string stepper, bool clSinglePrecision, unsigned int platformID, unsigned int deviceID,
+          const std::string clodeRoot);
+    virtual ~CLODE();
+
+    void setProblemInfo(ProblemInfo prob);
+    void setStepper(std::string newStepper);
+    void setPrecision(bool clSinglePrecision);
+    void setOpenCL(OpenCLResource opencl);
+    void setOpenCL(unsigned int platformID, unsigned int deviceID);
+
+    virtual void buildCL();
+
+    void setProblemData(std::vector<cl_double> newX0, std::vector<cl_double> newPars);
+    void setTspan(std::vector<cl_double> newTspan);
+    void setX0(std::vector<cl_double> newX0);
+    void setPars(std::vector<cl_double> newPars);
+    void setSolverParams(SolverParams<cl_double> newSp);
+
+    void seedRNG();
+    void seedRNG(cl_int mySeed);
+
+    void transient();
+
+    void shiftTspan();
+    void shiftX0();
+
+    const ProblemInfo getProblemInfo() const { return prob; }
+    const std::vector<cl_double> getTspan() const { return tspan; }
+    const SolverParams<cl_double> getSolverParams() const { return sp; }
+    const std::vector<cl_double> getPars() const { return pars; }
+    const std::vector<cl_double> getX0();
+    const std::vector<cl_double> getXf();
+    const std::vector<cl_double> getDt();
+    const std::vector<cl_double> getTf();
+    const std::vector<std::string> getAvailableSteppers() const { return availableSteppers; }
+
+    const std::string getProgramString() const { return buildOptions + clprogramstring + ODEsystemsource; }
+    void printStatus();
+
+    // additions (not in the reference): measurement hooks used by bench/tests
+    double getLastKernelMilliseconds() const;
+    std::vector<unsigned int> getStepCounts();
+    std::vector<cl_ulong> getRNGstate();
+};

@@ -103,7 +103,7 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.work_queue = d->work_queue != 0;
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
-    s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4;
+    s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4; // 0 = chosen at build time (clode_sim_build)
     return CLODE_OK;
 }
 
@@ -404,7 +404,19 @@ struct clode_sim {
     }
 
     // launch `f` over the ensemble; when `timed_first`, (re)start the event pair
-    int launch(CUfunction f, const char *what, bool first, bool last)
+    bool pending = false; // kernels enqueued, events recorded, not yet waited for
+
+    int wait(const char *what)
+    {
+        if (!pending) return CLODE_OK;
+        pending = false;
+        int rc = cu(d->cuStreamSynchronize(stream), what);
+        if (rc) return rc;
+        d->cuEventElapsedTime(&last_ms, ev0, ev1);
+        return CLODE_OK;
+    }
+
+    int launch(CUfunction f, const char *what, bool first, bool last, bool blocking = true)
     {
         if (!f) return fail(CLODE_ERR_STATE, std::string(what) + ": kernel not built");
         if (n == 0) return fail(CLODE_ERR_STATE, std::string(what) + ": no problem data set (nPts == 0)");
@@ -423,8 +435,8 @@ struct clode_sim {
         ++launches;
         if (last) {
             if ((rc = cu(d->cuEventRecord(ev1, stream), "cuEventRecord"))) return rc;
-            if ((rc = cu(d->cuStreamSynchronize(stream), what))) return rc;
-            d->cuEventElapsedTime(&last_ms, ev0, ev1);
+            pending = true;
+            if (blocking) return wait(what);
         }
         return CLODE_OK;
     }
@@ -635,28 +647,16 @@ int clode_sim_destroy(clode_sim *s)
     return CLODE_OK;
 }
 
-int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
+// load one compiled module into the simulation object and look up its kernels
+static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<char> &cubin, int *max_local_bytes)
 {
-    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
-    ProgramSpec spec;
-    int rc = parse_desc(desc, spec);
-    if (rc) return rc;
-    std::vector<char> cubin;
-    std::string log;
-    rc = compile_spec(spec, cubin, log);
-    s->build_log = rc ? g_error : log;
-    if (rc) return rc;
-
-    clode_sim::Scope scope(s);
-    const bool layout_changed = !s->built || spec.single != s->spec.single || spec.n_var != s->spec.n_var ||
-                                spec.n_par != s->spec.n_par || spec.n_aux != s->spec.n_aux;
+    int rc;
     if (s->module) {
         s->d->cuStreamSynchronize(s->stream);
         s->d->cuModuleUnload(s->module);
         s->module = nullptr;
     }
     s->k_transient = s->k_init = s->k_features = s->k_trajectory = s->k_layout = nullptr;
-    s->built = false;
     if ((rc = s->cu(s->d->cuModuleLoadData(&s->module, cubin.data()), "cuModuleLoadData"))) return rc;
     {
         size_t sym_bytes = 0;
@@ -668,6 +668,56 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_init, s->module, "clode_initialize_observer"), "clode_initialize_observer"))) return rc;
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_features, s->module, "clode_features"), "clode_features"))) return rc;
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_layout, s->module, "clode_observer_layout"), "clode_observer_layout"))) return rc;
+    }
+    if (spec.kernels & CLODE_KERNEL_TRAJECTORY) {
+        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_trajectory, s->module, "clode_trajectory"), "clode_trajectory"))) return rc;
+    }
+    int worst = 0;
+    CUfunction hot[] = {s->k_transient, s->k_features, s->k_trajectory};
+    for (CUfunction f : hot) {
+        int local = 0;
+        if (f) s->d->cuFuncGetAttribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
+        worst = std::max(worst, local);
+    }
+    *max_local_bytes = worst;
+    return CLODE_OK;
+}
+
+int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    ProgramSpec spec;
+    int rc = parse_desc(desc, spec);
+    if (rc) return rc;
+
+    clode_sim::Scope scope(s);
+    const bool layout_changed = !s->built || spec.single != s->spec.single || spec.n_var != s->spec.n_var ||
+                                spec.n_par != s->spec.n_par || spec.n_aux != s->spec.n_aux;
+    s->built = false;
+
+    // Register budget.  With min_blocks_per_sm == 0 the runtime picks the highest occupancy target
+    // that does not spill: the time loop is latency-bound on dependent FP64 chains, so resident warps
+    // matter (C2: 12 -> 20 warps/SM was +12 %), but spilling RK stages to local memory costs more than
+    // it gains.  Candidates are tried from 5 blocks/SM (<= 96 registers at 128 threads) downwards;
+    // every variant lands in the cubin cache.
+    std::vector<int> candidates;
+    if (desc->min_blocks_per_sm > 0) candidates.push_back(spec.min_blocks);
+    else {
+        const int most = std::max(1, 640 / spec.block);
+        for (int m = most; m >= 1; --m) candidates.push_back(m);
+    }
+    std::string log;
+    for (size_t k = 0; k < candidates.size(); ++k) {
+        spec.min_blocks = candidates[k];
+        std::vector<char> cubin;
+        rc = compile_spec(spec, cubin, log);
+        s->build_log = rc ? g_error : log;
+        if (rc) return rc;
+        int spilled = 0;
+        if ((rc = load_module(s, spec, cubin, &spilled))) return rc;
+        if (spilled <= 16 || k + 1 == candidates.size()) break;
+    }
+    if (spec.kernels & CLODE_KERNEL_FEATURES) {
         // ask the module how many observer-state rows it needs
         CUdeviceptr tmp = 0;
         if ((rc = s->cu(s->d->cuMemAlloc(&tmp, 16), "cuMemAlloc"))) return rc;
@@ -680,17 +730,12 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
         if (rc) return rc;
         s->od_nreal = host[0]; s->od_nuint = host[1]; s->two_pass = host[2];
     }
-    if (spec.kernels & CLODE_KERNEL_TRAJECTORY) {
-        if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_trajectory, s->module, "clode_trajectory"), "clode_trajectory"))) return rc;
-    }
     s->n_features = observer_feature_count(spec.observer, spec.n_var, spec.n_aux, spec.n_store);
     s->real_size = spec.single ? 4 : 8;
     if (layout_changed) s->free_ensemble(); // precision / dimension change invalidates device data
-    // a different observer or event-list length changes the observer-state layout
-    if (s->built == false) {
-        s->release(s->od_real); s->release(s->od_uint); s->release(s->F);
-        s->observer_initialized = false;
-    }
+    // a rebuilt program may have a different observer-state layout: drop it
+    s->release(s->od_real); s->release(s->od_uint); s->release(s->F);
+    s->observer_initialized = false;
     s->spec = spec;
     s->built = true;
     return CLODE_OK;
@@ -818,13 +863,14 @@ int clode_sim_get_rng_state(clode_sim *s, uint64_t *state, size_t count)
     return s->cu(s->d->cuMemcpyDtoH(state, s->rng.ptr, 8 * count), "get_rng_state");
 }
 
-int clode_sim_transient(clode_sim *s)
+static int run_transient(clode_sim *s, bool blocking)
 {
     if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
     if (!s->built) return fail(CLODE_ERR_STATE, "transient: program not built");
     clode_sim::Scope scope(s);
-    return s->launch(s->k_transient, "clode_transient", true, true);
+    return s->launch(s->k_transient, "clode_transient", true, true, blocking);
 }
+int clode_sim_transient(clode_sim *s) { return run_transient(s, true); }
 
 static int ensure_feature_buffers(clode_sim *s)
 {
@@ -854,7 +900,9 @@ int clode_sim_initialize_observer(clode_sim *s)
     return rc;
 }
 
-int clode_sim_features(clode_sim *s, int initialize)
+static int run_features(clode_sim *s, int initialize, bool blocking);
+int clode_sim_features(clode_sim *s, int initialize) { return run_features(s, initialize, true); }
+static int run_features(clode_sim *s, int initialize, bool blocking)
 {
     if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
     if (!s->built || !s->k_features) return fail(CLODE_ERR_STATE, "features: features kernels not built");
@@ -870,7 +918,7 @@ int clode_sim_features(clode_sim *s, int initialize)
         s->observer_initialized = true;
         first = false;
     }
-    return s->launch(s->k_features, "clode_features", first, true);
+    return s->launch(s->k_features, "clode_features", first, true, blocking);
 }
 
 int clode_sim_observer_initialized(clode_sim *s, int *flag)
@@ -880,7 +928,9 @@ int clode_sim_observer_initialized(clode_sim *s, int *flag)
     return CLODE_OK;
 }
 
-int clode_sim_trajectory(clode_sim *s)
+static int run_trajectory(clode_sim *s, bool blocking);
+int clode_sim_trajectory(clode_sim *s) { return run_trajectory(s, true); }
+static int run_trajectory(clode_sim *s, bool blocking)
 {
     if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
     if (!s->built || !s->k_trajectory) return fail(CLODE_ERR_STATE, "trajectory: trajectory kernel not built");
@@ -903,7 +953,24 @@ int clode_sim_trajectory(clode_sim *s)
         if ((rc = s->alloc(s->n_stored, 4 * s->n, "nStored"))) return rc;
         s->tr_rows = rows;
     }
-    return s->launch(s->k_trajectory, "clode_trajectory", true, true);
+    return s->launch(s->k_trajectory, "clode_trajectory", true, true, blocking);
+}
+
+int clode_sim_enqueue(clode_sim *s, int kernel, int initialize)
+{
+    switch (kernel) {
+    case CLODE_KERNEL_TRANSIENT: return run_transient(s, false);
+    case CLODE_KERNEL_FEATURES: return run_features(s, initialize, false);
+    case CLODE_KERNEL_TRAJECTORY: return run_trajectory(s, false);
+    }
+    return fail(CLODE_ERR_INVALID, "enqueue: unknown kernel id");
+}
+
+int clode_sim_wait(clode_sim *s)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    clode_sim::Scope scope(s);
+    return s->wait("wait");
 }
 
 int clode_sim_shift_x0(clode_sim *s)

@@ -143,6 +143,13 @@ CLODE_API int clode_sim_observer_initialized(clode_sim *sim, int *flag);
 CLODE_API int clode_sim_trajectory(clode_sim *sim);           /* CLODEtrajectory::trajectory (:97-130)          */
 CLODE_API int clode_sim_shift_x0(clode_sim *sim);             /* CLODE::shiftX0 (CLODE.cpp:502-515), device to device */
 
+/* Non-blocking variants, for callers that drive several GPUs from one thread (one clode_sim per
+ * device, the reference's unused `OpenCLResource(platformID, std::vector<deviceIDs>)` hook,
+ * OpenCLResource.hpp:104): enqueue on every shard, then wait on every shard.  `kernel` is one of
+ * CLODE_KERNEL_*; `initialize` as in clode_sim_features. */
+CLODE_API int clode_sim_enqueue(clode_sim *sim, int kernel, int initialize);
+CLODE_API int clode_sim_wait(clode_sim *sim);
+
 /* results: which = one of CLODE_BUF_*; out has `count` doubles (checked) */
 enum {
     CLODE_BUF_X0 = 0, CLODE_BUF_PARS = 1, CLODE_BUF_XF = 2, CLODE_BUF_DT = 3, CLODE_BUF_TF = 4,
