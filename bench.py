@@ -198,7 +198,7 @@ def run_ours(args):
     keep_p, pars = pinned(w["pars"])
     keep_dt, dt0 = pinned(np.full(n, w["solver"]["dt"]))
     sim.set_problem(x0, pars)
-    sim.seed_rng(1, rank * n, n_total)
+    sim.seed_rng(1, rank * n, n_total)  # global seeding rule: shards reproduce the unsharded streams
     nfeat = sim.n_features()
     step_row = {"basic": 5}.get(w["observer"], nfeat - (1 if w["observer"] in ("basicall", "localmax") else 4))
 
@@ -208,19 +208,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    fptr, fbytes, _ = None, None, None
-    gathered = None
-
     def gather_features():
         """the one exchange step of the path: features of every shard to rank 0 over NVLink (NCCL)"""
-        nonlocal gathered
         if not dist:
-            return
+            return None
+        from clode_b200 import sharding
         ptr, nbytes, _ = sim.device_buffer(_rt.BUF_F)
         local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
-        if rank == 0 and gathered is None:
-            gathered = [torch.empty_like(local_f) for _ in range(world)]
-        dist.gather(local_f, gathered if rank == 0 else None, dst=0)
+        return sharding.gather_rows(local_f, nfeat, n_total)
 
     def hot_step():
         sim.set_dt(dt0)          # per-instance dt persists across calls (reference semantics): reset it

@@ -1,0 +1,56 @@
+"""Host-side logic of the one-process-per-GPU path: instance-range partition, slicing of the
+variable-major ensemble arrays, and the single exchange step — the final gather of per-shard result
+matrices to rank 0 (NCCL over NVLink on GPU tensors, gloo on CPU tensors in the tests).
+
+Instances are independent, so nothing else is communicated.  The in-process
+multi-GPU path of the C++ classes (CLODE::setNpts) uses the same contiguous, warp-aligned ranges.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+def partition(n_total: int, world: int, rank: int, align: int = 32) -> Tuple[int, int]:
+    """[lo, hi) of `rank`: contiguous chunks of ceil(n/world) rounded up to `align` (the last may be short or empty)"""
+    chunk = -(-n_total // world)
+    chunk = -(-chunk // align) * align
+    lo = min(rank * chunk, n_total)
+    return lo, min(lo + chunk, n_total)
+
+
+def shard_rows(flat: np.ndarray, rows: int, n_total: int, lo: int, hi: int) -> np.ndarray:
+    """[rows][n_total] flat -> [rows][hi-lo] flat"""
+    return np.ascontiguousarray(np.asarray(flat).reshape(rows, n_total)[:, lo:hi]).ravel()
+
+
+def seed_states(seed: int, n_total: int, lo: int, hi: int) -> np.ndarray:
+    """RNG state words of instances [lo, hi) under the reference's global rule RNGstate[k] = seed + k
+    (clode/cpp/CLODE.cpp:447-453): instance i owns words i and n_total + i"""
+    i = np.arange(lo, hi, dtype=np.int64)
+    return np.concatenate([(np.int64(seed) + i).astype(np.uint64), (np.int64(seed) + np.int64(n_total) + i).astype(np.uint64)])
+
+
+def gather_rows(local, rows: int, n_total: int, dst: int = 0):
+    """Gather per-rank [rows][n_local] tensors into [rows][n_total] on `dst` (None elsewhere).
+    `local` is a 1-D torch tensor (CPU for gloo, CUDA for NCCL); ranks may hold different n_local."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [partition(n_total, world, r) for r in range(world)]
+    widest = max(hi - lo for lo, hi in counts)
+    lo, hi = counts[rank]
+    padded = torch.zeros(rows * widest, dtype=local.dtype, device=local.device)
+    if hi > lo:
+        padded.view(rows, widest)[:, : hi - lo] = local.view(rows, hi - lo)
+    parts: Optional[List] = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, parts, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty(rows, n_total, dtype=local.dtype, device=local.device)
+    for (plo, phi), part in zip(counts, parts):
+        if phi > plo:
+            out[:, plo:phi] = part.view(rows, widest)[:, : phi - plo]
+    return out.reshape(-1)

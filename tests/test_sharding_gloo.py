@@ -1,0 +1,70 @@
+"""N > 1 host path on CPU: two processes (gloo), each integrates its shard of a stochastic ensemble
+with the CPU oracle standing in for the GPU kernels, the feature matrices are gathered on rank 0 and
+must equal the unsharded run bit for bit — which requires the global RNG seeding rule, the
+variable-major slicing and the gather re-layout to be right.  CPU only."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from clode_b200 import sharding
+from oracle import restate
+from oracle.common import Config, Observer, Solver
+from problems import ensemble
+
+N_TOTAL = 83  # not a multiple of anything
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _unsharded():
+    lib = restate.OracleLib(Config("lactotroph_noise", "seuler", "basicall", math="pm"))
+    ts, x0, pars = ensemble("lactotroph_noise", N_TOTAL)
+    sp = Solver(dt=0.01, max_steps=100000)
+    return lib.features((0.0, 3.0), x0, pars, sp, Observer(), np.full(N_TOTAL, sp.dt), sharding.seed_states(1, N_TOTAL, 0, N_TOTAL))
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = restate.OracleLib(Config("lactotroph_noise", "seuler", "basicall", math="pm"))
+    ts, x0, pars = ensemble("lactotroph_noise", N_TOTAL)
+    lo, hi = sharding.partition(N_TOTAL, world, rank)
+    sp = Solver(dt=0.01, max_steps=100000)
+    r = lib.features((0.0, 3.0), sharding.shard_rows(x0, 4, N_TOTAL, lo, hi), sharding.shard_rows(pars, 4, N_TOTAL, lo, hi),
+                     sp, Observer(), np.full(hi - lo, sp.dt), sharding.seed_states(1, N_TOTAL, lo, hi))
+    F = sharding.gather_rows(torch.from_numpy(r["F"]), lib.n_feat, N_TOTAL)
+    xf = sharding.gather_rows(torch.from_numpy(r["xf"]), 4, N_TOTAL)
+    rng = sharding.gather_rows(torch.from_numpy(r["rng"].view(np.int64)), 2, N_TOTAL)
+    if rank == 0:
+        np.savez(out_path, F=F.numpy(), xf=xf.numpy(), rng=rng.numpy().view(np.uint64))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_run_equals_unsharded(world, tmp_path):
+    restate.build(Config("lactotroph_noise", "seuler", "basicall", math="pm"))  # compile once, before forking
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got, want = np.load(out), _unsharded()
+    for k in ("F", "xf", "rng"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_partition_properties():
+    for n, world in [(1 << 20, 8), (83, 2), (83, 3), (5, 8), (64, 2), (0, 4)]:
+        spans = [sharding.partition(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % 32 == 0 or lo == n for lo, _ in spans)
+    i = np.arange(10, 20)
+    s = sharding.seed_states(-3, 100, 10, 20)
+    assert np.array_equal(s[:10].astype(np.int64), -3 + i) and np.array_equal(s[10:].astype(np.int64), 97 + i)
