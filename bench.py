@@ -5,7 +5,7 @@
 
 Workload (default C2 = BASELINE.json configs[1]): Lorenz system, `features` kernel, dopri5,
 observer `basic`, 2^20 parameter sets PER GPU (weak scaling: the global r-grid is N*2^20 points,
-rank g integrates the contiguous slice [g*2^20, (g+1)*2^20)), double precision, t in [0,100],
+rank g integrates the interleaved shard {g, g+N, g+2N, ...}, i.e. every GPU sees the same cost distribution), double precision, t in [0,100],
 dt0 = 0.01, dtmax = 1, abstol = reltol = 1e-6.  One "step" = one pass of the hot
 path (initializeObserver + features kernels) over the rank's ensemble.
 
@@ -41,12 +41,13 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: SMs x FP64 lanes x 
 
 
 # ------------------------------------------------------------------------------------------------
-def workload(name: str, n_total: int, lo: int, hi: int):
-    """inputs of instances [lo, hi) of a global ensemble of n_total (variable-major, float64)"""
+def workload(name: str, n_total: int, index):
+    """inputs of the instances `index` of a global ensemble of n_total (variable-major, float64)"""
     from clode_b200.flops import flops_per_step
 
-    n = hi - lo
-    frac = (np.arange(lo, hi, dtype=np.float64)) / max(n_total - 1, 1)
+    idx = np.asarray(index, dtype=np.int64)
+    n = idx.size
+    frac = idx.astype(np.float64) / max(n_total - 1, 1)
     if name == "C2":
         w = dict(model="lorenz63", stepper="dopri5", observer="basic", kind="features", tspan=(0.0, 100.0),
                  solver=dict(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, max_steps=10000000),
@@ -56,7 +57,6 @@ def workload(name: str, n_total: int, lo: int, hi: int):
     elif name == "C3":
         # 1024 x 1024 (gcal x gbk) grid, flattened row-major; bs23 + thresh2 (two-pass)
         side = int(round(n_total ** 0.5))
-        idx = np.arange(lo, hi)
         gcal = 0.5 + 3.5 * (idx // side) / max(side - 1, 1)
         gbk = 2.0 * (idx % side) / max(side - 1, 1)
         w = dict(model="lactotroph", stepper="bs23", observer="thresh2", kind="features", tspan=(0.0, 10000.0),
@@ -108,7 +108,7 @@ def cpu_reference(wname: str, n_total: int, steps: int, warmup: int, stride: int
     from oracle import ref, restate
     from oracle.common import Config, Observer, Solver, seed_states
 
-    w = workload(wname, n_total, 0, N_PER_GPU)
+    w = workload(wname, n_total, np.arange(0, N_PER_GPU))
     cfg = Config(w["model"], w["stepper"], w["observer"], contract="fast")
     if os.path.exists(ref.so_path(cfg)) or ref.reference_available():
         lib, kind = ref.RefLib(cfg), "reference"
@@ -143,7 +143,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": base["value"],
             "unit": "instance-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload(args.workload, N_PER_GPU, 0, 1)["desc"],
+            "data": "synthetic", "config": {"workload": workload(args.workload, N_PER_GPU, np.arange(1))["desc"],
                                             "note": "CPU arm runs a bounded sample; the metric is per instance-step"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "instance-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -178,7 +178,10 @@ def run_ours(args):
     build.build_runtime()
     n = N_PER_GPU if args.npts <= 0 else args.npts
     n_total = n * world
-    w = workload(args.workload, n_total, rank * n, (rank + 1) * n)
+    from clode_b200 import sharding
+    # cost-balanced interleaved shards of ONE global grid: rank g owns instances g, g+N, g+2N, ...
+    index = sharding.interleaved(n_total, world, rank)
+    w = workload(args.workload, n_total, index)
     nv, npar, na, nw = MODELS[w["model"]]
     prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"],
                        kernels=_rt.KERNEL_FEATURES, work_queue=bool(args.work_queue), block_size=args.block,
@@ -198,7 +201,7 @@ def run_ours(args):
     keep_p, pars = pinned(w["pars"])
     keep_dt, dt0 = pinned(np.full(n, w["solver"]["dt"]))
     sim.set_problem(x0, pars)
-    sim.seed_rng(1, rank * n, n_total)  # global seeding rule: shards reproduce the unsharded streams
+    sim.set_rng_state(sharding.seed_states_for(1, n_total, index))  # global seeding rule (CLODE.cpp:447-453)
     nfeat = sim.n_features()
     step_row = {"basic": 5}.get(w["observer"], nfeat - (1 if w["observer"] in ("basicall", "localmax") else 4))
 
@@ -212,10 +215,9 @@ def run_ours(args):
         """the one exchange step of the path: features of every shard to rank 0 over NVLink (NCCL)"""
         if not dist:
             return None
-        from clode_b200 import sharding
         ptr, nbytes, _ = sim.device_buffer(_rt.BUF_F)
         local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
-        return sharding.gather_rows(local_f, nfeat, n_total)
+        return sharding.gather_interleaved(local_f, nfeat, n_total)
 
     def hot_step():
         sim.set_dt(dt0)          # per-instance dt persists across calls (reference semantics): reset it

@@ -178,15 +178,13 @@ void CLODE::setNpts(cl_int newNpts)
     tf.resize(nPts);
     xf.resize(x0elements);
 
-    // contiguous instance ranges, one per GPU, multiples of the warp size
+    // interleaved shards, one per GPU
     const size_t g = shards().size();
-    size_t chunk = ((size_t)nPts + g - 1) / g;
-    chunk = (chunk + 31) / 32 * 32;
-    size_t offset = 0;
-    for (auto &s : shards()) {
-        s.offset = std::min(offset, (size_t)nPts);
-        s.count = std::min(chunk, (size_t)nPts - s.offset);
-        offset += chunk;
+    for (size_t k = 0; k < g; ++k) {
+        Shard &s = shards()[k];
+        s.first = k;
+        s.stride = g;
+        s.count = (size_t)nPts > k ? ((size_t)nPts - k + g - 1) / g : 0;
         check(clode_sim_set_npts(s.sim, s.count, sp.dt), "CLODE::setNpts");
     }
     onNptsChanged();
@@ -205,9 +203,7 @@ void CLODE::uploadRows(const std::vector<cl_double> &full, int rows, int (*sette
     std::vector<double> part;
     for (auto &s : shards()) {
         if (s.count == 0) continue;
-        part.resize((size_t)rows * s.count);
-        for (int r = 0; r < rows; ++r)
-            std::copy_n(full.begin() + (size_t)r * nPts + s.offset, s.count, part.begin() + (size_t)r * s.count);
+        takeShard(full, (size_t)nPts, rows, s, part);
         check(setter(s.sim, part.data(), part.size()), where);
     }
 }
@@ -225,8 +221,7 @@ void CLODE::downloadRows(std::vector<cl_double> &full, int rows, int which, cons
         if (s.count == 0) continue;
         part.resize((size_t)rows * s.count);
         check(clode_sim_get(s.sim, which, part.data(), part.size()), where);
-        for (int r = 0; r < rows; ++r)
-            std::copy_n(part.begin() + (size_t)r * s.count, s.count, full.begin() + (size_t)r * nPts + s.offset);
+        putShard(full, (size_t)nPts, rows, s, part);
     }
 }
 
@@ -303,6 +298,7 @@ void CLODE::setSolverParams(SolverParams<cl_double> newSp)
     lg::debug_("set SolverParams");
 }
 
+// push the host copy of the RNG state to the shards
 // CLODE::seedRNG() (CLODE.cpp:420-444): nRNGstate x nPts random 64-bit words
 void CLODE::seedRNG()
 {
@@ -313,20 +309,22 @@ void CLODE::seedRNG()
     std::vector<cl_ulong> part;
     for (auto &s : shards()) {
         if (s.count == 0) continue;
-        part.resize(2 * s.count);
-        for (int r = 0; r < 2; ++r)
-            std::copy_n(RNGstate.begin() + (size_t)r * nPts + s.offset, s.count, part.begin() + (size_t)r * s.count);
+        takeShard(RNGstate, (size_t)nPts, 2, s, part);
         check(clode_sim_set_rng_state(s.sim, part.data(), part.size()), "CLODE::seedRNG");
     }
     lg::debug_("set random RNG seed");
 }
 
-// CLODE::seedRNG(cl_int) (CLODE.cpp:447-465): word k of the global state array is seed + k
+// CLODE::seedRNG(cl_int) (CLODE.cpp:447-465): word k of the GLOBAL state array is seed + k, whatever the sharding
 void CLODE::seedRNG(cl_int mySeed)
 {
     for (size_t i = 0; i < RNGstate.size(); ++i) RNGstate[i] = (cl_ulong)(mySeed + (cl_int)i);
-    for (auto &s : shards())
-        if (s.count) check(clode_sim_seed_rng(s.sim, mySeed, s.offset, (uint64_t)nPts), "CLODE::seedRNG(int mySeed)");
+    std::vector<cl_ulong> part;
+    for (auto &s : shards()) {
+        if (s.count == 0) continue;
+        takeShard(RNGstate, (size_t)nPts, 2, s, part);
+        check(clode_sim_set_rng_state(s.sim, part.data(), part.size()), "CLODE::seedRNG(int mySeed)");
+    }
     lg::debug_("set fixed RNG seed");
 }
 
@@ -405,9 +403,13 @@ double CLODE::getLastKernelMilliseconds() const
 
 std::vector<unsigned int> CLODE::getStepCounts()
 {
-    std::vector<unsigned int> out(nPts);
-    for (auto &s : shards())
-        if (s.count) check(clode_sim_get_steps(s.sim, out.data() + s.offset, s.count), "CLODE::getStepCounts");
+    std::vector<unsigned int> out(nPts), part;
+    for (auto &s : shards()) {
+        if (s.count == 0) continue;
+        part.resize(s.count);
+        check(clode_sim_get_steps(s.sim, part.data(), s.count), "CLODE::getStepCounts");
+        putShard(out, (size_t)nPts, 1, s, part);
+    }
     return out;
 }
 
@@ -418,8 +420,7 @@ std::vector<cl_ulong> CLODE::getRNGstate()
         if (s.count == 0) continue;
         part.resize(2 * s.count);
         check(clode_sim_get_rng_state(s.sim, part.data(), part.size()), "CLODE::getRNGstate");
-        for (int r = 0; r < 2; ++r)
-            std::copy_n(part.begin() + (size_t)r * s.count, s.count, RNGstate.begin() + (size_t)r * nPts + s.offset);
+        putShard(RNGstate, (size_t)nPts, 2, s, part);
     }
     return RNGstate;
 }

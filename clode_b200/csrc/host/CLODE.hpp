@@ -67,12 +67,25 @@ protected:
 
     std::string clprogramstring, buildOptions, ODEsystemsource;
 
-    // ---- runtime objects: one per GPU, each owning instances [offset, offset + count) ----
+    // ---- runtime objects: one per GPU.  Shard g of G owns instances g, g+G, g+2G, ... (cost-balanced:
+    // sweeps are usually sorted grids whose cost varies smoothly, so contiguous ranges would load the GPUs
+    // unevenly); on its GPU a shard is stored contiguously, so device accesses stay coalesced.
     struct Shard {
         clode_sim *sim = nullptr;
         int device = 0;
-        size_t offset = 0, count = 0;
+        size_t first = 0, stride = 1, count = 0; // global instance of local column k: first + k * stride
     };
+    template <typename T> static void takeShard(const std::vector<T> &full, size_t nTotal, int rows, const Shard &s, std::vector<T> &part)
+    {
+        part.resize((size_t)rows * s.count);
+        for (int r = 0; r < rows; ++r)
+            for (size_t k = 0; k < s.count; ++k) part[(size_t)r * s.count + k] = full[(size_t)r * nTotal + s.first + k * s.stride];
+    }
+    template <typename T> static void putShard(std::vector<T> &full, size_t nTotal, int rows, const Shard &s, const std::vector<T> &part)
+    {
+        for (int r = 0; r < rows; ++r)
+            for (size_t k = 0; k < s.count; ++k) full[(size_t)r * nTotal + s.first + k * s.stride] = part[(size_t)r * s.count + k];
+    }
     struct Runtime; // owns the clode_sim handles; shared so that copies of a CLODE stay valid
     std::shared_ptr<Runtime> runtime;
     std::vector<Shard> &shards();

@@ -61,8 +61,7 @@ void CLODEtrajectory::downloadStored(std::vector<cl_double> &full, int width, in
         if (s.count == 0) continue;
         part.resize(rows * width * s.count);
         check(clode_sim_get(s.sim, which, part.data(), part.size()), where);
-        for (size_t r = 0; r < rows * width; ++r)
-            std::copy_n(part.begin() + r * s.count, s.count, full.begin() + r * nPts + s.offset);
+        putShard(full, (size_t)nPts, (int)(rows * width), s, part);
     }
 }
 
@@ -74,7 +73,12 @@ std::vector<cl_double> CLODEtrajectory::getAux() { downloadStored(aux, nAux, CLO
 std::vector<cl_int> CLODEtrajectory::getNstored()
 {
     nStored.resize(nPts);
-    for (auto &s : shards())
-        if (s.count) check(clode_sim_get_n_stored(s.sim, nStored.data() + s.offset, s.count), "CLODEtrajectory::getNstored");
+    std::vector<cl_int> part;
+    for (auto &s : shards()) {
+        if (s.count == 0) continue;
+        part.resize(s.count);
+        check(clode_sim_get_n_stored(s.sim, part.data(), s.count), "CLODEtrajectory::getNstored");
+        putShard(nStored, (size_t)nPts, 1, s, part);
+    }
     return nStored;
 }

@@ -20,6 +20,48 @@ def partition(n_total: int, world: int, rank: int, align: int = 32) -> Tuple[int
     return lo, min(lo + chunk, n_total)
 
 
+def interleaved(n_total: int, world: int, rank: int) -> np.ndarray:
+    """Cost-balanced assignment: rank g owns instances g, g+world, g+2*world, ...  Parameter sweeps are
+    usually sorted grids whose cost varies smoothly along the grid (Lorenz r-sweep: 300 steps at r<1, 6500 in
+    the chaotic band), so contiguous ranges load the GPUs unevenly while every interleaved shard sees the
+    same cost distribution.  On its own GPU a shard is still stored contiguously (coalesced)."""
+    return np.arange(rank, n_total, world, dtype=np.int64)
+
+
+def take_rows(flat: np.ndarray, rows: int, n_total: int, index: np.ndarray) -> np.ndarray:
+    """[rows][n_total] flat -> [rows][len(index)] flat for an arbitrary instance index set"""
+    return np.ascontiguousarray(np.asarray(flat).reshape(rows, n_total)[:, index]).ravel()
+
+
+def seed_states_for(seed: int, n_total: int, index: np.ndarray) -> np.ndarray:
+    """global seeding rule (clode/cpp/CLODE.cpp:447-453) for an arbitrary instance index set"""
+    i = np.asarray(index, dtype=np.int64)
+    return np.concatenate([(np.int64(seed) + i).astype(np.uint64), (np.int64(seed) + np.int64(n_total) + i).astype(np.uint64)])
+
+
+def gather_interleaved(local, rows: int, n_total: int, dst: int = 0):
+    """gather_rows for interleaved shards: rank g's column k is global instance g + k*world"""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    widest = -(-n_total // world)
+    mine = len(range(rank, n_total, world))
+    padded = torch.zeros(rows * widest, dtype=local.dtype, device=local.device)
+    if mine:
+        padded.view(rows, widest)[:, :mine] = local.view(rows, mine)
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, parts, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty(rows, n_total, dtype=local.dtype, device=local.device)
+    for g, part in enumerate(parts):
+        cnt = len(range(g, n_total, world))
+        if cnt:
+            out[:, g::world] = part.view(rows, widest)[:, :cnt]
+    return out.reshape(-1)
+
+
 def shard_rows(flat: np.ndarray, rows: int, n_total: int, lo: int, hi: int) -> np.ndarray:
     """[rows][n_total] flat -> [rows][hi-lo] flat"""
     return np.ascontiguousarray(np.asarray(flat).reshape(rows, n_total)[:, lo:hi]).ravel()

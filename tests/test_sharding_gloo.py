@@ -32,28 +32,33 @@ def _unsharded():
     return lib.features((0.0, 3.0), x0, pars, sp, Observer(), np.full(N_TOTAL, sp.dt), sharding.seed_states(1, N_TOTAL, 0, N_TOTAL))
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, layout):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = restate.OracleLib(Config("lactotroph_noise", "seuler", "basicall", math="pm"))
     ts, x0, pars = ensemble("lactotroph_noise", N_TOTAL)
-    lo, hi = sharding.partition(N_TOTAL, world, rank)
+    if layout == "contiguous":
+        lo, hi = sharding.partition(N_TOTAL, world, rank)
+        index, gather = np.arange(lo, hi), sharding.gather_rows
+    else:
+        index, gather = sharding.interleaved(N_TOTAL, world, rank), sharding.gather_interleaved
     sp = Solver(dt=0.01, max_steps=100000)
-    r = lib.features((0.0, 3.0), sharding.shard_rows(x0, 4, N_TOTAL, lo, hi), sharding.shard_rows(pars, 4, N_TOTAL, lo, hi),
-                     sp, Observer(), np.full(hi - lo, sp.dt), sharding.seed_states(1, N_TOTAL, lo, hi))
-    F = sharding.gather_rows(torch.from_numpy(r["F"]), lib.n_feat, N_TOTAL)
-    xf = sharding.gather_rows(torch.from_numpy(r["xf"]), 4, N_TOTAL)
-    rng = sharding.gather_rows(torch.from_numpy(r["rng"].view(np.int64)), 2, N_TOTAL)
+    r = lib.features((0.0, 3.0), sharding.take_rows(x0, 4, N_TOTAL, index), sharding.take_rows(pars, 4, N_TOTAL, index),
+                     sp, Observer(), np.full(index.size, sp.dt), sharding.seed_states_for(1, N_TOTAL, index))
+    F = gather(torch.from_numpy(r["F"]), lib.n_feat, N_TOTAL)
+    xf = gather(torch.from_numpy(r["xf"]), 4, N_TOTAL)
+    rng = gather(torch.from_numpy(r["rng"].view(np.int64)), 2, N_TOTAL)
     if rank == 0:
         np.savez(out_path, F=F.numpy(), xf=xf.numpy(), rng=rng.numpy().view(np.uint64))
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("layout", ["contiguous", "interleaved"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_run_equals_unsharded(world, tmp_path):
+def test_sharded_run_equals_unsharded(world, layout, tmp_path):
     restate.build(Config("lactotroph_noise", "seuler", "basicall", math="pm"))  # compile once, before forking
     out = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out, layout), nprocs=world, join=True)
     got, want = np.load(out), _unsharded()
     for k in ("F", "xf", "rng"):
         assert np.array_equal(got[k], want[k]), k
