@@ -197,6 +197,11 @@ def run_ours(args):
         v = t.numpy()
         v[:] = a
         return t, v
+    if args.shuffle:
+        perm = np.random.default_rng(args.shuffle).permutation(n)
+        w["pars"] = w["pars"].reshape(npar, n)[:, perm].ravel()
+        w["x0"] = w["x0"].reshape(nv, n)[:, perm].ravel()
+        w["desc"] += ", grid order shuffled"
     keep_x0, x0 = pinned(w["x0"])
     keep_p, pars = pinned(w["pars"])
     keep_dt, dt0 = pinned(np.full(n, w["solver"]["dt"]))
@@ -316,6 +321,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shuffle", type=int, default=0, help="randomly permute the parameter grid (heterogeneous warps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -138,136 +138,177 @@ CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams
 #endif
 }
 
-// index of the instance this thread works on first, and how it gets the next one
-struct WorkSource {
-    size_t n;
-#ifdef CLODE_WORK_QUEUE
-    unsigned long long *head;
-    // warp-aggregated fetch: one atomic per warp per refill round
-    __device__ __forceinline__ size_t next()
-    {
-        const unsigned int active = __activemask();
-        const int leader = __ffs(active) - 1;
-        const int lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(head, (unsigned long long)__popc(active));
-        base = __shfl_sync(active, base, leader);
-        return (size_t)(base + __popc(active & ((1u << lane) - 1u)));
-    }
-    __device__ __forceinline__ size_t first() { return next(); }
-#else
-    __device__ __forceinline__ size_t first() { return blockIdx.x * (size_t)blockDim.x + threadIdx.x; }
-    __device__ __forceinline__ size_t next() { return n; }
+// ------------------------------------------------------------------------------------------
+// Ensemble drivers.  A "job" is one instance's life inside a kernel: begin(i) loads it,
+// live() says whether another attempt is due, attempt() performs one, end(i) writes results.
+//
+//  * default: thread <-> instance, grid = ceil(n / block).  The attempt loop keeps the lanes of
+//    a warp in step; a lane whose instance is finished idles until the warp's slowest lane is done.
+//  * CLODE_WORK_QUEUE: persistent threads with PER-LANE REFILL.  The grid is sized to the
+//    device (SMs x resident blocks); every warp keeps looping while any lane has work, and when
+//    __ballot_sync shows at least CLODE_REFILL_LANES idle lanes (or the whole warp is idle) the idle
+//    lanes take the next unprocessed instances from a global counter — one warp-aggregated atomicAdd
+//    per refill — and load them while the busy lanes wait.  Results are indexed by instance id, so
+//    they do not depend on which lane integrated what.  This pays when instances of one warp have very
+//    different step counts (shuffled or randomly sampled parameter sets); for sorted grids the plain
+//    mapping is already >96 % lane-efficient (profiles/).
+#ifndef CLODE_REFILL_LANES
+#define CLODE_REFILL_LANES 8
 #endif
-};
 
-CLODE_DEV WorkSource work_source(const KernelArgs &a)
+template <class Job> CLODE_DEV void run_ensemble(const KernelArgs &a, Job &job)
 {
-    WorkSource w;
-    w.n = a.n;
-#ifdef CLODE_WORK_QUEUE
-    w.head = a.queue;
+#ifndef CLODE_WORK_QUEUE
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    job.begin(i);
+    while (job.live())
+        job.attempt();
+    job.end(i);
+#else
+    const unsigned int FULL = 0xffffffffu;
+    const unsigned int lane = threadIdx.x & 31u;
+    size_t i = 0;
+    bool have = false;    // this lane holds an unfinished instance
+    bool drained = false; // the queue has been seen empty (warp-uniform)
+    for (;;) {
+        const unsigned int idle = __ballot_sync(FULL, !have);
+        if (idle == FULL && drained) break;
+        if (!drained && (idle == FULL || __popc(idle) >= CLODE_REFILL_LANES)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            drained = base + __popc(idle) >= a.n;
+            if (!have) {
+                i = (size_t)(base + __popc(idle & ((1u << lane) - 1u)));
+                if (i < a.n) {
+                    job.begin(i);
+                    have = true;
+                }
+            }
+        }
+        if (have) {
+            if (job.live())
+                job.attempt();
+            if (!job.live()) {
+                job.end(i);
+                have = false;
+            }
+        }
+    }
 #endif
-    return w;
 }
 
-// ------------------------------------------------------------------------------------------
+// ---- transient (clode/cpp/transient.cl:9-77) -------------------------------------------------
+struct TransientJob {
+    const KernelArgs &a;
+    SolverParams sp;
+    Controller ctl;
+    realtype t_end;
+    Instance I;
+    unsigned int step;
+    realtype h;
+    bool clean;
+    __device__ __forceinline__ TransientJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); step = 0; h = I.dt; clean = true; }
+    __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps; }
+    __device__ __forceinline__ void attempt() { if (advance(I, h, clean, sp, ctl, t_end)) ++step; }
+    __device__ __forceinline__ void end(size_t i) { store_instance(I, a, i, step); }
+};
+
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
 clode_transient()
 {
-    const KernelArgs &a = clode_args;
-    const SolverParams sp = solver_params(a);
-    const Controller ctl = make_controller(sp);
-    const realtype t_end = (realtype)a.t1;
-    WorkSource work = work_source(a);
-    for (size_t i = work.first(); i < a.n; i = work.next()) {
-        Instance I;
-        load_instance(I, a, i);
-        unsigned int step = 0;
-        realtype h = I.dt;
-        bool clean = true;
-        while (I.t <= t_end && step < sp.max_steps) {
-            if (advance(I, h, clean, sp, ctl, t_end))
-                ++step;
-        }
-        store_instance(I, a, i, step);
-    }
+    TransientJob job(clode_args);
+    run_ensemble(clode_args, job);
 }
 
 #ifdef CLODE_WITH_FEATURES
-// ------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_initialize_observer()
-{
-    const KernelArgs &a = clode_args;
-    const SolverParams sp = solver_params(a);
-    const Controller ctl = make_controller(sp);
-    const ObserverParams op = observer_params(a);
-    const realtype t_end = (realtype)a.t1;
-    WorkSource work = work_source(a);
-    for (size_t i = work.first(); i < a.n; i = work.next()) {
-        Instance I;
-        load_instance(I, a, i);
-        Observer ob;
-        ob.init(I);
-#if CLODE_TWO_PASS
-        {
-            unsigned int step = 0;
-            realtype h = I.dt;
-            bool clean = true;
-            while (I.t < t_end && step < sp.max_steps) { // strict '<' (initializeObserver.cl:62)
-                if (advance(I, h, clean, sp, ctl, t_end)) {
-                    ++step;
-                    ob.warmup(I, op);
-                }
-            }
-            // rewind; dt and the RNG state are NOT written back (initializeObserver.cl:72-82)
-            I.t = (realtype)a.t0;
-            const realtype *x0 = (const realtype *)a.x0;
-#pragma unroll
-            for (int j = 0; j < NV; ++j)
-                I.x[j] = x0[(size_t)j * a.n + i];
-            getRHS(I.t, I.x, I.p, I.k1, I.aux, I.w);
+// ---- initializeObserver (clode/cpp/initializeObserver.cl:9-83) -------------------------------
+struct WarmupJob {
+    const KernelArgs &a;
+    SolverParams sp;
+    ObserverParams op;
+    Controller ctl;
+    realtype t_end;
+    Instance I;
+    Observer ob;
+    unsigned int step;
+    realtype h;
+    bool clean;
+    __device__ __forceinline__ WarmupJob(const KernelArgs &a_)
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); ob.init(I); step = 0; h = I.dt; clean = true; }
+    // strict '<' (initializeObserver.cl:62); one-pass observers do no warm-up integration at all
+    __device__ __forceinline__ bool live() const { return CLODE_TWO_PASS && I.t < t_end && step < sp.max_steps; }
+    __device__ __forceinline__ void attempt()
+    {
+        if (advance(I, h, clean, sp, ctl, t_end)) {
+            ++step;
+            ob.warmup(I, op);
         }
+    }
+    __device__ __forceinline__ void end(size_t i)
+    {
+#if CLODE_TWO_PASS
+        // rewind; dt and the RNG state are NOT written back (initializeObserver.cl:72-82)
+        I.t = (realtype)a.t0;
+        const realtype *x0 = (const realtype *)a.x0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            I.x[j] = x0[(size_t)j * a.n + i];
+        getRHS(I.t, I.x, I.p, I.k1, I.aux, I.w);
 #endif
         ob.arm(I, op);
         ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
         ob.visit(st);
     }
-}
+};
 
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_features()
+clode_initialize_observer()
 {
-    const KernelArgs &a = clode_args;
-    const SolverParams sp = solver_params(a);
-    const Controller ctl = make_controller(sp);
-    const ObserverParams op = observer_params(a);
-    const realtype t_end = (realtype)a.t1;
-    WorkSource work = work_source(a);
-    for (size_t i = work.first(); i < a.n; i = work.next()) {
-        Instance I;
+    WarmupJob job(clode_args);
+    run_ensemble(clode_args, job);
+}
+
+// ---- features (clode/cpp/features.cl:10-106) ---------------------------------------------------
+struct FeaturesJob {
+    const KernelArgs &a;
+    SolverParams sp;
+    ObserverParams op;
+    Controller ctl;
+    realtype t_end;
+    Instance I;
+    Observer ob;
+    unsigned int step;
+    realtype h;
+    bool clean, alive;
+    __device__ __forceinline__ FeaturesJob(const KernelArgs &a_)
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ void begin(size_t i)
+    {
         load_instance(I, a, i);
-        Observer ob;
-        {
-            ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
-            ob.visit(ld);
+        ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit(ld);
+        step = 0; h = I.dt; clean = true;
+        alive = I.t <= t_end && step < sp.max_steps;
+    }
+    __device__ __forceinline__ bool live() const { return alive; }
+    __device__ __forceinline__ void attempt()
+    {
+        if (advance(I, h, clean, sp, ctl, t_end)) {
+            ++step;
+            // features.cl:71-81: update, then event test, then event features (a terminal event ends the run)
+            ob.update(I, op);
+            bool terminal = false;
+            if (ob.event(I, op))
+                terminal = ob.on_event(I, op);
+            alive = !terminal && I.t <= t_end && step < sp.max_steps;
         }
-        unsigned int step = 0;
-        realtype h = I.dt;
-        bool clean = true;
-        bool live = I.t <= t_end && step < sp.max_steps;
-        while (live) {
-            if (advance(I, h, clean, sp, ctl, t_end)) {
-                ++step;
-                // features.cl:71-81: update, then event test, then event features
-                ob.update(I, op);
-                bool terminal = false;
-                if (ob.event(I, op))
-                    terminal = ob.on_event(I, op);
-                live = !terminal && I.t <= t_end && step < sp.max_steps;
-            }
-        }
+    }
+    __device__ __forceinline__ void end(size_t i)
+    {
         FeatureOut out = {(realtype *)a.F, (size_t)a.n, i, 0};
         ob.emit(out);
         ob.rebase(I.t - (realtype)a.t0);
@@ -275,6 +316,13 @@ clode_features()
         ob.visit(st);
         store_instance(I, a, i, step);
     }
+};
+
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_features()
+{
+    FeaturesJob job(clode_args);
+    run_ensemble(clode_args, job);
 }
 
 // number of observer-state rows, for the host allocator
@@ -290,7 +338,7 @@ extern "C" __global__ void clode_observer_layout(int *out)
 #endif // CLODE_WITH_FEATURES
 
 #ifdef CLODE_WITH_TRAJECTORY
-// ------------------------------------------------------------------------------------------
+// ---- trajectory (clode/cpp/trajectory.cl:14-112) -----------------------------------------------
 // Row r of the outputs holds stored point r of every instance:
 //   t[r*n + i], x[(r*N_VAR + j)*n + i], dx[...], aux[(r*N_AUX + j)*n + i].
 // A warp therefore writes one contiguous 32*sizeof(realtype) segment per variable per row.
@@ -298,7 +346,7 @@ extern "C" __global__ void clode_observer_layout(int *out)
 CLODE_DEV void store_point(const Instance &I, const KernelArgs &a, const size_t i, const size_t row)
 {
     const size_t n = a.n;
-    ((realtype *)a.tr_t)[row * n + i] = I.t;
+    __stcs((realtype *)a.tr_t + row * n + i, I.t);
     realtype *x = (realtype *)a.tr_x + row * n * NV + i;
     realtype *dx = (realtype *)a.tr_dx + row * n * NV + i;
 #pragma unroll
@@ -314,34 +362,46 @@ CLODE_DEV void store_point(const Instance &I, const KernelArgs &a, const size_t 
 #endif
 }
 
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
-clode_trajectory()
-{
-    const KernelArgs &a = clode_args;
-    const SolverParams sp = solver_params(a);
-    const Controller ctl = make_controller(sp);
-    const realtype t_end = (realtype)a.t1;
-    WorkSource work = work_source(a);
-    for (size_t i = work.first(); i < a.n; i = work.next()) {
-        Instance I;
+struct TrajectoryJob {
+    const KernelArgs &a;
+    SolverParams sp;
+    Controller ctl;
+    realtype t_end;
+    Instance I;
+    size_t inst;
+    unsigned int step, row;
+    realtype h;
+    bool clean;
+    __device__ __forceinline__ TrajectoryJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ void begin(size_t i)
+    {
         load_instance(I, a, i);
-        unsigned int row = 0;
+        inst = i; step = 0; row = 0; h = I.dt; clean = true;
         store_point(I, a, i, 0);
-        unsigned int step = 0;
-        realtype h = I.dt;
-        bool clean = true;
-        while (I.t <= t_end && step < sp.max_steps && row < sp.max_store) {
-            if (advance(I, h, clean, sp, ctl, t_end)) {
-                ++step;
-                if (step % sp.nout == 0) {
-                    ++row;
-                    store_point(I, a, i, row);
-                }
+    }
+    __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps && row < sp.max_store; }
+    __device__ __forceinline__ void attempt()
+    {
+        if (advance(I, h, clean, sp, ctl, t_end)) {
+            ++step;
+            if (step % sp.nout == 0) {
+                ++row;
+                store_point(I, a, inst, row);
             }
         }
+    }
+    __device__ __forceinline__ void end(size_t i)
+    {
         a.n_stored[i] = (int)row;
         store_instance(I, a, i, step);
     }
+};
+
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_trajectory()
+{
+    TrajectoryJob job(clode_args);
+    run_ensemble(clode_args, job);
 }
 #endif // CLODE_WITH_TRAJECTORY
 

@@ -254,3 +254,59 @@ def test_cuda_abi_error_behaviour(rt):
     with pytest.raises(rt.RtError):  # wrong-sized x0
         sim.set_x0(np.ones(5))
     sim.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# persistent-thread work queue with per-lane refill: results must not depend on which lane ran what
+@pytest.mark.parametrize("model,stepper,observer,kind", [
+    ("lorenz63", "dopri5", "localmax", "features"),
+    ("lactotroph", "bs23", "thresh2", "features"),   # two-pass: the warm-up kernel also runs from the queue
+    ("lorenz63", "dopri5", "basic", "transient"),
+    ("chay_keizer", "dopri5", "basic", "trajectory"),
+    ("lactotroph_noise", "seuler", "basicall", "features"),
+])
+def test_cuda_work_queue_lane_refill_bit_exact(rt, model, stepper, observer, kind):
+    n = 5000 + 13  # many refill rounds per warp, ragged tail
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[1] / 8)
+    rng_perm = np.random.default_rng(5).permutation(n)  # shuffle: heterogeneous step counts inside every warp
+    nv = len(x0) // n
+    npar = len(pars) // n
+    x0 = x0.reshape(nv, n)[:, rng_perm].ravel()
+    pars = pars.reshape(npar, n)[:, rng_perm].ravel()
+    ns = 2 if observer in ("localmax", "thresh2") else 0
+    fixed = stepper == "seuler"
+    sp = Solver(dt=0.01 if fixed else 0.1, dtmax=10.0, abstol=1e-6, reltol=1e-4, max_steps=200000, max_store=40, nout=3)
+    op = Observer(max_event_count=8, max_event_timestamps=ns, x_up_threshold=0.3, x_down_threshold=0.2)
+    plain = GpuRun(rt, model, stepper, observer, ns, bit_exact=True, work_queue=False)
+    queue = GpuRun(rt, model, stepper, observer, ns, bit_exact=True, work_queue=True)
+    out = []
+    for g in (plain, queue):
+        g.setup(ts, x0, pars, sp, op if kind == "features" else None, seed=2)
+        out.append(g.run(kind))
+        g.close()
+    a, b = out
+    if kind == "trajectory":
+        rows = a["rows"]
+        stored = np.arange(rows)[:, None] <= a["n_stored"][None, :]
+        for k, width in (("t", 1), ("x", nv), ("dx", nv)):
+            m = np.broadcast_to(stored[:, None, :], (rows, width, n))
+            assert np.array_equal(a[k].reshape(rows, width, n)[m], b[k].reshape(rows, width, n)[m]), k
+        assert_bit_equal(b, a, "queue vs plain", keys=["n_stored", "xf", "tf", "dt", "rng", "steps"])
+    else:
+        assert_bit_equal(b, a, "queue vs plain")
+    assert a["steps"].max() > 2 * max(int(np.median(a["steps"])), 1) or stepper == "seuler"  # really heterogeneous
+    # and both equal the oracle on a sample of instances
+    sub = np.arange(0, n, 97)
+    lib = restate.OracleLib(Config(model, stepper, observer if kind == "features" else "basic", ns if kind == "features" else 0, math="pm"))
+    pick = lambda v, w: np.asarray(v).reshape(w, n)[:, sub].ravel()
+    dt, rng = np.full(sub.size, sp.dt), pick(seed_states(2, n), 2)
+    if kind == "features":
+        o = lib.features(ts, pick(x0, nv), pick(pars, npar), sp, op, dt, rng)
+        assert np.array_equal(pick(b["F"], len(b["F"]) // n), o["F"])
+    elif kind == "transient":
+        o = lib.transient(ts, pick(x0, nv), pick(pars, npar), sp, dt, rng)
+    else:
+        o = lib.trajectory(ts, pick(x0, nv), pick(pars, npar), sp, dt, rng)
+        assert np.array_equal(b["n_stored"][sub], o["n_stored"])
+    assert np.array_equal(pick(b["xf"], nv), o["xf"]) and np.array_equal(pick(b["rng"], 2), o["rng"])
