@@ -65,6 +65,19 @@ def workload(name: str, n_total: int, index):
                  pars=np.concatenate([gcal, np.full(n, 3.0), gbk]),
                  x0=np.concatenate([np.full(n, -60.0), np.zeros(n), np.zeros(n), np.full(n, 0.1)]),
                  desc="C3: lactotroph thresh2 features, bs23, 1024x1024 grid per GPU, f64")
+    elif name in ("C5", "C5e"):
+        # Chay-Keizer trajectories: 512 x 512 (gca x kpmca) grid per GPU, 2000 stored points, nout = 1
+        side = int(round(n_total ** 0.5))
+        gca = 550.0 + 500.0 * (idx // side) / max(side - 1, 1)
+        kpmca = 0.095 + 0.06 * (idx % side) / max(side - 1, 1)
+        stepper = "rk4" if name == "C5" else "euler"
+        w = dict(model="chay_keizer", stepper=stepper, observer="basic", kind="trajectory", tspan=(0.0, 1000.0),
+                 solver=dict(dt=0.5 if name == "C5" else 0.05, dtmax=1.0, abstol=1e-6, reltol=1e-4, max_steps=10000000,
+                             max_store=2000, nout=1),
+                 observer_params=dict(),
+                 pars=np.concatenate([gca, np.full(n, 750.0), kpmca]),
+                 x0=np.concatenate([np.full(n, -50.0), np.full(n, 0.01), np.full(n, 0.12)]),
+                 desc=f"C5: Chay-Keizer trajectory, {stepper}, 2000 stored points x 2^18 instances per GPU, nout=1, f64")
     else:
         raise SystemExit(f"unknown workload {name}")
     w["flops_per_step"] = flops_per_step(w["stepper"], w["model"])
@@ -176,16 +189,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     build.build_runtime()
-    n = N_PER_GPU if args.npts <= 0 else args.npts
+    n = (N_PER_GPU if not args.workload.startswith("C5") else 1 << 18) if args.npts <= 0 else args.npts
     n_total = n * world
     from clode_b200 import sharding
     # cost-balanced interleaved shards of ONE global grid: rank g owns instances g, g+N, g+2N, ...
     index = sharding.interleaved(n_total, world, rank)
     w = workload(args.workload, n_total, index)
     nv, npar, na, nw = MODELS[w["model"]]
+    is_traj = w["kind"] == "trajectory"
     prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"],
-                       kernels=_rt.KERNEL_FEATURES, work_queue=bool(args.work_queue), block_size=args.block,
-                       min_blocks_per_sm=args.min_blocks)
+                       kernels=_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES,
+                       work_queue=bool(args.work_queue), block_size=args.block, min_blocks_per_sm=args.min_blocks,
+                       staged_trajectory=bool(args.staged))
     sim = _rt.Sim(prog, device=local)
     sim.set_solver_params(**w["solver"])
     sim.set_observer_params(**w["observer_params"])
@@ -207,7 +222,7 @@ def run_ours(args):
     keep_dt, dt0 = pinned(np.full(n, w["solver"]["dt"]))
     sim.set_problem(x0, pars)
     sim.set_rng_state(sharding.seed_states_for(1, n_total, index))  # global seeding rule (CLODE.cpp:447-453)
-    nfeat = sim.n_features()
+    nfeat = sim.n_features() if not is_traj else nv  # trajectory: the gathered / fetched result is xf
     step_row = {"basic": 5}.get(w["observer"], nfeat - (1 if w["observer"] in ("basicall", "localmax") else 4))
 
     def barrier():
@@ -220,13 +235,16 @@ def run_ours(args):
         """the one exchange step of the path: features of every shard to rank 0 over NVLink (NCCL)"""
         if not dist:
             return None
-        ptr, nbytes, _ = sim.device_buffer(_rt.BUF_F)
+        ptr, nbytes, _ = sim.device_buffer(_rt.BUF_XF if is_traj else _rt.BUF_F)
         local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
         return sharding.gather_interleaved(local_f, nfeat, n_total)
 
     def hot_step():
         sim.set_dt(dt0)          # per-instance dt persists across calls (reference semantics): reset it
-        sim.features(1)          # initializeObserver + features kernels, synchronous
+        if is_traj:
+            sim.trajectory()     # trajectory kernel, synchronous
+        else:
+            sim.features(1)      # initializeObserver + features kernels, synchronous
         ms = sim.last_kernel_ms()
         gather_features()
         return ms
@@ -256,12 +274,19 @@ def run_ours(args):
         sim.set_x0(x0)
         sim.set_pars(pars)
         sim.set_dt(dt0)
-        sim.features(1)
-        F = sim.get_f()
+        if is_traj:
+            # the e2e result read back is the final state; the 29 GB trajectory itself stays on the device
+            # (fetching it is a separate API call, CLODEtrajectory::getX)
+            sim.trajectory()
+            F = sim.get_xf()
+        else:
+            sim.features(1)
+            F = sim.get_f()
         gather_features()
     barrier()
     e2e_s = time.perf_counter() - t0
-    assert int(F.reshape(nfeat, n)[step_row].sum()) == steps_per_pass
+    if not is_traj:
+        assert int(F.reshape(nfeat, n)[step_row].sum()) == steps_per_pass
     h2d = 8 * n * (nv + npar + 1)
     d2h = 8 * n * nfeat
 
@@ -284,8 +309,25 @@ def run_ours(args):
     value = total_steps_per_pass * args.steps / (dev_ms * 1e-3)
     peak_tf, _ = _rt.measure_fp64_peak(local, 5)
     achieved_tf = w["flops_per_step"] * steps_per_pass * args.steps / (sum(kernel_ms) * 1e-3) / 1e12
-    info = sim.kernel_info(_rt.KERNEL_FEATURES)
-    base, _ = cpu_reference(args.workload, n_total, 1, 1) if not args.no_cpu_baseline else (None, None)
+    info = sim.kernel_info(_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES)
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": "DFMA micro-benchmark measured on this GPU in this run (clode_measure_fp64_peak)",
+                "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+                "flops_per_step": w["flops_per_step"]}
+    if is_traj:
+        from clode_b200.flops import trajectory_bytes_per_point
+        stored = int(sim.get_trajectory_counts().astype(np.int64).sum()) + n  # + the initial point of every instance
+        per_point = trajectory_bytes_per_point(w["model"], na)
+        gbs = per_point * stored * args.steps / (sum(kernel_ms) * 1e-3) / 1e9
+        peaks_file = os.path.join(REPO, "MEASURED_PEAKS.json")
+        peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                    "bytes_per_stored_point": per_point, "stored_points": stored,
+                    "fp64": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf}}
+    base, _ = cpu_reference(args.workload, n_total, 1, 1) if not (args.no_cpu_baseline or is_traj) else (None, None)
     line = {
         "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": value, "unit": "instance-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
@@ -297,11 +339,7 @@ def run_ours(args):
         "e2e": {"value": total_steps_per_pass * args.steps / e2e_s, "unit": "instance-steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
-                     "peak_source": "DFMA micro-benchmark measured on this GPU in this run (clode_measure_fp64_peak)",
-                     "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
-                     "flops_per_step": w["flops_per_step"]},
+        "roofline": roofline,
         "cpu_baseline": base,
     }
     print(json.dumps(line), flush=True)
@@ -321,6 +359,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--staged", type=int, default=0, help="trajectory: shared-memory staged TMA bulk stores")
     ap.add_argument("--shuffle", type=int, default=0, help="randomly permute the parameter grid (heterogeneous warps)")
     args = ap.parse_args()
     if args.impl == "reference":

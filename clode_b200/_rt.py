@@ -34,7 +34,7 @@ class ProgramDesc(ctypes.Structure):
         ("n_aux", ctypes.c_int), ("n_wiener", ctypes.c_int), ("f_var_ix", ctypes.c_int),
         ("e_var_ix", ctypes.c_int), ("n_store_events", ctypes.c_int), ("kernels", ctypes.c_int),
         ("bit_exact", ctypes.c_int), ("work_queue", ctypes.c_int), ("block_size", ctypes.c_int),
-        ("min_blocks_per_sm", ctypes.c_int),
+        ("min_blocks_per_sm", ctypes.c_int), ("staged_trajectory", ctypes.c_int),
     ]
 
 
@@ -125,12 +125,14 @@ class Program:
     work_queue: bool = False
     block_size: int = 0
     min_blocks_per_sm: int = 0
+    staged_trajectory: bool = False
 
     def c(self) -> ProgramDesc:
         return ProgramDesc(self.rhs_source.encode(), self.stepper.encode(), self.observer.encode(),
                            int(self.single_precision), self.n_var, self.n_par, self.n_aux, self.n_wiener,
                            self.f_var_ix, self.e_var_ix, self.n_store_events, self.kernels,
-                           int(self.bit_exact), int(self.work_queue), self.block_size, self.min_blocks_per_sm)
+                           int(self.bit_exact), int(self.work_queue), self.block_size, self.min_blocks_per_sm,
+                           int(self.staged_trajectory))
 
 
 def compile_program(prog: Program) -> tuple[bytes, str]:
@@ -284,6 +286,11 @@ class Sim:
         _check(self._lib.clode_sim_get_n_stored(self._h, nst.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n)))
         return dict(t=self.get(BUF_T, rows * n), x=self.get(BUF_X, rows * n * nv), dx=self.get(BUF_DX, rows * n * nv),
                     aux=self.get(BUF_AUX, rows * n * na) if na else np.zeros(1), n_stored=nst, rows=rows)
+
+    def get_trajectory_counts(self):
+        nst = np.empty(self.n, np.int32)
+        _check(self._lib.clode_sim_get_n_stored(self._h, nst.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(self.n)))
+        return nst
 
     def get_steps(self):
         out = np.empty(self.n, np.uint32)

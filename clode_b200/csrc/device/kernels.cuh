@@ -397,12 +397,111 @@ struct TrajectoryJob {
     }
 };
 
+#if defined(CLODE_TRAJ_STAGED) && !CLODE_ADAPTIVE && !defined(CLODE_WORK_QUEUE)
+// ---- shared-memory staged stores (fixed-step methods) ------------------------------------------
+// With a fixed-step method every instance of a block reaches stored row r in the same loop iteration,
+// so the block's values for one (row, variable) line are CLODE_BLOCK consecutive reals in global memory.
+// The threads write their values into a double-buffered shared-memory tile [lines][CLODE_BLOCK]; one
+// thread then hands each line to the TMA as a bulk shared->global copy (cp.async.bulk, `UBLKCP` in SASS),
+// which drains asynchronously while the block integrates the next step: the store traffic leaves the
+// LSU / issue path of the compute warps entirely.  Lanes that finished earlier leave stale values in
+// their columns; those land in rows beyond their own nStored, which the API never returns.
+#define TRAJ_LINES (1 + 2 * N_VAR + N_AUX)
+
+CLODE_DEV void tile_put(realtype (*tile)[CLODE_BLOCK], const Instance &I)
+{
+    const unsigned int c = threadIdx.x;
+    tile[0][c] = I.t;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        tile[1 + j][c] = I.x[j];
+        tile[1 + NV + j][c] = I.k1[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N_AUX; ++j)
+        tile[1 + 2 * NV + j][c] = I.aux[j];
+}
+
+// one thread: bulk-copy every line of the tile to row `row` of the outputs, `cols` valid columns
+CLODE_DEV void tile_flush(realtype (*tile)[CLODE_BLOCK], const KernelArgs &a, const size_t base, const size_t row,
+                          const unsigned int cols)
+{
+    const size_t n = a.n;
+    const unsigned int bytes = cols * (unsigned int)sizeof(realtype);
+#pragma unroll
+    for (int line = 0; line < TRAJ_LINES; ++line) {
+        realtype *g;
+        if (line == 0) g = (realtype *)a.tr_t + row * n + base;
+        else if (line < 1 + NV) g = (realtype *)a.tr_x + (row * NV + (line - 1)) * n + base;
+        else if (line < 1 + 2 * NV) g = (realtype *)a.tr_dx + (row * NV + (line - 1 - NV)) * n + base;
+        else g = (realtype *)a.tr_aux + (row * N_AUX + (line - 1 - 2 * NV)) * n + base;
+        const unsigned int src = (unsigned int)__cvta_generic_to_shared(&tile[line][0]);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+clode_trajectory()
+{
+    const KernelArgs &a = clode_args;
+    __shared__ __align__(128) realtype tile[2][TRAJ_LINES][CLODE_BLOCK];
+    const size_t base = blockIdx.x * (size_t)blockDim.x;
+    const size_t i = base + threadIdx.x;
+    const bool valid = i < a.n;
+    const unsigned int cols = (unsigned int)(a.n - base < (size_t)CLODE_BLOCK ? a.n - base : (size_t)CLODE_BLOCK);
+    // bulk copies need 16-byte aligned addresses and sizes: even row pitch and an even column count
+    const bool bulk_ok = (a.n * sizeof(realtype)) % 16 == 0 && (cols * sizeof(realtype)) % 16 == 0;
+    TrajectoryJob job(a);
+    if (!bulk_ok) { // rare shapes: plain per-thread stores
+        if (valid) {
+            job.begin(i);
+            while (job.live()) job.attempt();
+            job.end(i);
+        }
+        return;
+    }
+    if (valid) {
+        load_instance(job.I, a, i);
+        job.inst = i; job.step = 0; job.row = 0; job.h = job.I.dt; job.clean = true;
+        tile_put(tile[0], job.I);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) tile_flush(tile[0], a, base, 0, cols);
+    int buf = 1;
+    for (unsigned int k = 1;; ++k) {
+        const bool live = valid && job.live();
+        if (!__syncthreads_or(live)) break;
+        if (live) {
+            step_fixed(job.I);
+            ++job.step;
+        }
+        if (k % job.sp.nout == 0) { // block-uniform: every live lane stores row k / nout now
+            // the buffer about to be overwritten was handed to the TMA two stores ago: wait until it has been read
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+            if (live) {
+                ++job.row;
+                tile_put(tile[buf], job.I);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) tile_flush(tile[buf], a, base, (size_t)(k / job.sp.nout), cols);
+            buf ^= 1;
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (valid) job.end(i);
+}
+#else
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
 clode_trajectory()
 {
     TrajectoryJob job(clode_args);
     run_ensemble(clode_args, job);
 }
+#endif
 #endif // CLODE_WITH_TRAJECTORY
 
 #endif // CLODE_KERNELS_CUH

@@ -77,7 +77,7 @@ struct ProgramSpec {
     int n_var = 0, n_par = 0, n_aux = 0, n_wiener = 0;
     int f_var = 0, e_var = 0, n_store = 0;
     int kernels = CLODE_KERNEL_TRANSIENT;
-    bool bit_exact = false, work_queue = false;
+    bool bit_exact = false, work_queue = false, staged = false;
     int block = 128, min_blocks = 4;
 };
 
@@ -101,6 +101,7 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.bit_exact = d->bit_exact != 0;
     if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
     s.work_queue = d->work_queue != 0;
+    s.staged = d->staged_trajectory != 0;
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
     s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4; // 0 = chosen at build time (clode_sim_build)
@@ -131,6 +132,7 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.kernels & CLODE_KERNEL_TRAJECTORY) o.push_back("-DCLODE_WITH_TRAJECTORY");
     if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
+    if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     return o;
 }
 

@@ -84,7 +84,9 @@ typedef struct clode_program_desc {
     int bit_exact;            /* 1: portable transcendental math + no FMA contraction (parity tier)     */
     int work_queue;           /* 1: persistent threads pulling instances from a global queue            */
     int block_size;           /* threads per block; 0 = default                                          */
-    int min_blocks_per_sm;    /* __launch_bounds__ second argument; 0 = default                          */
+    int min_blocks_per_sm;    /* __launch_bounds__ second argument; 0 = chosen by spill check            */
+    int staged_trajectory;    /* 1: trajectory rows staged in shared memory and written by TMA bulk copies
+                                 (fixed-step methods); 0: per-thread coalesced stores                     */
 } clode_program_desc;
 
 /* compile only (no GPU needed): returns malloc'd cubin + log; caller frees with clode_free */

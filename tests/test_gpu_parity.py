@@ -310,3 +310,30 @@ def test_cuda_work_queue_lane_refill_bit_exact(rt, model, stepper, observer, kin
         o = lib.trajectory(ts, pick(x0, nv), pick(pars, npar), sp, dt, rng)
         assert np.array_equal(b["n_stored"][sub], o["n_stored"])
     assert np.array_equal(pick(b["xf"], nv), o["xf"]) and np.array_equal(pick(b["rng"], 2), o["rng"])
+
+
+# ----------------------------------------------------------------------------------------------
+# trajectory rows staged in shared memory and written with TMA bulk copies (fixed-step methods)
+@pytest.mark.parametrize("model,stepper,n,nout,max_store", [
+    ("chay_keizer", "rk4", 1000, 1, 50),      # nout = 1, stops on max_store
+    ("chay_keizer", "euler", 258, 3, 400),    # last block partially filled, stops on t_end
+    ("thompson_a1", "heun", 131, 2, 60),      # odd n: alignment fallback to per-thread stores
+    ("lactotroph_noise", "seuler", 512, 4, 30),
+])
+def test_cuda_staged_trajectory_bit_exact(rt, model, stepper, n, nout, max_store):
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[0] + (ts[1] - ts[0]) / 10)
+    sp = Solver(dt=0.05, dtmax=1.0, max_steps=100000, max_store=max_store, nout=nout)
+    lib = restate.OracleLib(Config(model, stepper, math="pm"))
+    o = run_oracle(lib, "trajectory", ts, x0, pars, sp, None, seed=4)
+    g = GpuRun(rt, model, stepper, bit_exact=True, staged=True)
+    g.setup(ts, x0, pars, sp, None, seed=4)
+    r = g.trajectory()
+    rows, nv, na = o["rows"], lib.n_var, lib.n_aux
+    stored = np.arange(rows)[:, None] <= o["n_stored"][None, :]
+    for k, width in (("t", 1), ("x", nv), ("dx", nv), ("aux", na)):
+        if width:
+            m = np.broadcast_to(stored[:, None, :], (rows, width, n))
+            assert np.array_equal(r[k].reshape(rows, width, n)[m], o[k].reshape(rows, width, n)[m]), k
+    assert_bit_equal(r, o, "staged trajectory", keys=["n_stored", "xf", "tf", "dt", "rng"])
+    g.close()
