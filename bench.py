@@ -65,6 +65,14 @@ def workload(name: str, n_total: int, index):
                  pars=np.concatenate([gcal, np.full(n, 3.0), gbk]),
                  x0=np.concatenate([np.full(n, -60.0), np.zeros(n), np.zeros(n), np.full(n, 0.1)]),
                  desc="C3: lactotroph thresh2 features, bs23, 1024x1024 grid per GPU, f64")
+    elif name == "C4":
+        # lactotroph + current noise, Euler-Maruyama, identical parameters, per-instance RNG streams
+        w = dict(model="lactotroph_noise", stepper="seuler", observer="basicall", kind="features", tspan=(0.0, 100.0),
+                 solver=dict(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-4, max_steps=10000000),
+                 observer_params=dict(),
+                 pars=np.concatenate([np.full(n, 1.5), np.full(n, 3.0), np.full(n, 1.0), np.full(n, 1.0)]),
+                 x0=np.concatenate([np.full(n, -60.0), np.zeros(n), np.zeros(n), np.full(n, 0.1)]),
+                 desc="C4: lactotroph_noise stochastic Euler features (basicall), per-instance RNG streams, f64")
     elif name in ("C5", "C5e"):
         # Chay-Keizer trajectories: 512 x 512 (gca x kpmca) grid per GPU, 2000 stored points, nout = 1
         side = int(round(n_total ** 0.5))
@@ -189,7 +197,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     build.build_runtime()
-    n = (N_PER_GPU if not args.workload.startswith("C5") else 1 << 18) if args.npts <= 0 else args.npts
+    default_n = {"C5": 1 << 18, "C5e": 1 << 18, "C4": 1 << 22}.get(args.workload, N_PER_GPU)
+    n = default_n if args.npts <= 0 else args.npts
     n_total = n * world
     from clode_b200 import sharding
     # cost-balanced interleaved shards of ONE global grid: rank g owns instances g, g+N, g+2N, ...
@@ -310,8 +319,12 @@ def run_ours(args):
     peak_tf, _ = _rt.measure_fp64_peak(local, 5)
     achieved_tf = w["flops_per_step"] * steps_per_pass * args.steps / (sum(kernel_ms) * 1e-3) / 1e12
     info = sim.kernel_info(_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    # (profiles/r01_*_summary.txt); None for workloads that were not captured
+    ncu_traffic = {"C2": 144.456192e6 + 121.891584e6, "C5": 21.757184e6 + 29.332668e9, "C5e": 18.968832e6 + 29.331877e9}
+    traffic = ncu_traffic.get(args.workload) if n == default_n else None
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": "DFMA micro-benchmark measured on this GPU in this run (clode_measure_fp64_peak)",
                 "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
                 "flops_per_step": w["flops_per_step"]}
@@ -323,7 +336,7 @@ def run_ours(args):
         peaks_file = os.path.join(REPO, "MEASURED_PEAKS.json")
         peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
         hbm = peaks.get("hbm_gbs", 6650.0)
-        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)",
                     "bytes_per_stored_point": per_point, "stored_points": stored,
                     "fp64": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf}}
