@@ -697,16 +697,26 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
                                 spec.n_par != s->spec.n_par || spec.n_aux != s->spec.n_aux;
     s->built = false;
 
-    // Register budget.  With min_blocks_per_sm == 0 the runtime picks the highest occupancy target
-    // that does not spill: the time loop is latency-bound on dependent FP64 chains, so resident warps
-    // matter (C2: 12 -> 20 warps/SM was +12 %), but spilling RK stages to local memory costs more than
-    // it gains.  Candidates are tried from 5 blocks/SM (<= 96 registers at 128 threads) downwards;
-    // every variant lands in the cubin cache.
+    // Register budget.  With min_blocks_per_sm == 0 the runtime picks the occupancy target from the
+    // spill size of each candidate: the time loop is latency-bound on dependent FP64 chains, so resident
+    // warps matter, and moderate spills (L1-resident) cost less than they buy.  Rule distilled from the
+    // round-1 sweeps (profiles/r01_sweep_*.log, r01_c3c4_occupancy_sweep.log), for 128-thread blocks:
+    //   5 blocks/SM (<= 96 regs) if nothing spills          (C2 Lorenz dopri5 basic: best)
+    //   4 blocks/SM (<= 128 regs) if spills <= 1 KiB/thread  (C3 lactotroph thresh2: +13 %, C4 seuler: +34 %)
+    //   3 blocks/SM if spills <= 2 KiB, else 2, else 1.
+    // Every variant lands in the cubin cache, so the search is paid once per program.
     std::vector<int> candidates;
-    if (desc->min_blocks_per_sm > 0) candidates.push_back(spec.min_blocks);
-    else {
+    std::vector<int> spill_limit;
+    if (desc->min_blocks_per_sm > 0) {
+        candidates.push_back(spec.min_blocks);
+        spill_limit.push_back(1 << 30);
+    } else {
         const int most = std::max(1, 640 / spec.block);
-        for (int m = most; m >= 1; --m) candidates.push_back(m);
+        for (int m = most; m >= 1; --m) {
+            candidates.push_back(m);
+            const int warps = m * spec.block / 32;
+            spill_limit.push_back(warps >= 20 ? 16 : warps >= 16 ? 1024 : warps >= 12 ? 2048 : 1 << 30);
+        }
     }
     std::string log;
     for (size_t k = 0; k < candidates.size(); ++k) {
@@ -717,7 +727,7 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
         if (rc) return rc;
         int spilled = 0;
         if ((rc = load_module(s, spec, cubin, &spilled))) return rc;
-        if (spilled <= 16 || k + 1 == candidates.size()) break;
+        if (spilled <= spill_limit[k] || k + 1 == candidates.size()) break;
     }
     if (spec.kernels & CLODE_KERNEL_FEATURES) {
         // ask the module how many observer-state rows it needs
