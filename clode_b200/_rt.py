@@ -262,13 +262,18 @@ class Sim:
         _check(self._lib.clode_sim_shift_x0(self._h))
 
     # ---- results -----------------------------------------------------------------------
-    def get(self, which: int, count: int):
-        out = np.empty(count, np.float64)
+    def get(self, which: int, count: int, out: np.ndarray | None = None):
+        """download `count` reals of buffer `which`; pass a preallocated (ideally pinned) float64 `out` to avoid
+        a pageable bounce buffer on large transfers"""
+        if out is None:
+            out = np.empty(count, np.float64)
+        elif out.dtype != np.float64 or out.size < count or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array with at least `count` elements")
         _check(self._lib.clode_sim_get(self._h, which, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(count)))
-        return out
+        return out[:count] if out.size != count else out
 
     def get_x0(self): return self.get(BUF_X0, self.n * self.prog.n_var)
-    def get_xf(self): return self.get(BUF_XF, self.n * self.prog.n_var)
+    def get_xf(self, out=None): return self.get(BUF_XF, self.n * self.prog.n_var, out)
     def get_dt(self): return self.get(BUF_DT, self.n)
     def get_tf(self): return self.get(BUF_TF, self.n)
 
@@ -277,7 +282,7 @@ class Sim:
         _check(self._lib.clode_sim_n_features(self._h, ctypes.byref(k)))
         return k.value
 
-    def get_f(self): return self.get(BUF_F, self.n * self.n_features())
+    def get_f(self, out=None): return self.get(BUF_F, self.n * self.n_features(), out)
 
     def get_trajectory(self):
         rows = self._sp.max_store + 1
