@@ -136,3 +136,28 @@ def test_c5_trajectory_2000_points_x_256k(rt):
         assert np.array_equal(got[: 2001 * width].ravel(), o[key].reshape(rows * width, sub.size)[: 2001 * width].ravel()), key
     assert np.array_equal(sim.get_xf().reshape(nv, n)[:, sub].ravel(), o["xf"])
     sim.close()
+
+
+def test_c1_van_der_pol_rk4_transient_4096(rt):
+    """BASELINE config 1 in full: Van der Pol, transient, rk4 dt = 0.01, t in [0, 100], 4096-point mu grid, double —
+    the oracle integrates all of it, so the comparison is exhaustive (bit-exact tier) and toleranced (production)."""
+    from problems import ensemble
+    n = 4096
+    ts, x0, pars = ensemble("vanderpol", n)
+    sp = Solver(dt=0.01, max_steps=1000000)
+    lib_pm = restate.OracleLib(Config("vanderpol", "rk4", math="pm"))
+    o = lib_pm.transient(ts, x0, pars, sp, np.full(n, sp.dt), sharding.seed_states(1, n, 0, n), nthreads=8)
+    for bit_exact in (True, False):
+        sim = rt.Sim(rt.Program(rhs_source("vanderpol"), "rk4", 2, 1, 0, 0, kernels=rt.KERNEL_TRANSIENT, bit_exact=bit_exact))
+        sim.set_solver_params(dt=0.01, max_steps=1000000)
+        sim.set_tspan(*ts)
+        sim.set_problem(x0, pars)
+        sim.seed_rng(1)
+        sim.transient()
+        xf, tf, steps = sim.get_xf(), sim.get_tf(), sim.get_steps()
+        assert np.array_equal(tf, o["tf"]) and np.all(steps == steps[0]) and steps[0] in (10000, 10001)
+        if bit_exact:
+            assert np.array_equal(xf, o["xf"])
+        else:
+            assert np.allclose(xf, o["xf"], rtol=1e-8, atol=1e-10)  # FMA contraction over 10^4 steps, stiff for mu ~ 10
+        sim.close()
