@@ -34,12 +34,24 @@ struct ObserverParams {
 
 // ---- small building blocks -----------------------------------------------------------
 
-// engine-internal forms of runningMeanTime / runningMean (clODE_utilities.cl:167-177) whose division
-// goes through div_nr (IEEE in the reference-arithmetic builds, Newton reciprocal in production)
-CLODE_DEV realtype mean_time(realtype mean, realtype v, realtype dt, realtype span)
-{
-    return mean + div_nr((v - mean) * dt, span);
-}
+// engine-internal forms of runningMeanTime / runningMean (clODE_utilities.cl:167-177).
+// Reference-arithmetic builds evaluate mean + (v - mean) * dt / span exactly as written.  In the production
+// build the weight w = dt / span is formed once per step (div_nr) and every running mean of that step is
+// updated with one FMA, mean + (v - mean) * w: the observers keep 1 (basic) to nVar + nAux + 1 (thresh2)
+// such means, and an FP64 division each was a fifth of the per-step observer cost.
+#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH) || defined(__CUDACC_EMU__)
+struct MeanWeight {
+    realtype dt, span;
+};
+CLODE_DEV MeanWeight mean_weight(realtype dt, realtype span) { MeanWeight w = {dt, span}; return w; }
+CLODE_DEV realtype mean_time(realtype mean, realtype v, const MeanWeight &w) { return mean + (v - mean) * w.dt / w.span; }
+#else
+struct MeanWeight {
+    realtype w;
+};
+CLODE_DEV MeanWeight mean_weight(realtype dt, realtype span) { MeanWeight w = {div_nr(dt, span)}; return w; }
+CLODE_DEV realtype mean_time(realtype mean, realtype v, const MeanWeight &w) { return fma(v - mean, w.w, mean); }
+#endif
 CLODE_DEV void mean_count(realtype *mean, realtype v, unsigned int count)
 {
     if (count == 1) *mean = v;
@@ -93,13 +105,13 @@ struct Extents {
         for (int j = 0; j < N_AUX; ++j) { amax[j] = -BIG_REAL; amin[j] = BIG_REAL; amean[j] = ZERO; }
     }
     // time-weighted means (all observers except nhood1)
-    __device__ __forceinline__ void update_time(const Instance &I, realtype dt, realtype span)
+    __device__ __forceinline__ void update_time(const Instance &I, const MeanWeight &w)
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             xmax[j] = max_nn(I.x[j], xmax[j]);
             xmin[j] = min_nn(I.x[j], xmin[j]);
-            xmean[j] = mean_time(xmean[j], I.x[j], dt, span);
+            xmean[j] = mean_time(xmean[j], I.x[j], w);
             dxmax[j] = max_nn(I.k1[j], dxmax[j]);
             dxmin[j] = min_nn(I.k1[j], dxmin[j]);
         }
@@ -107,7 +119,7 @@ struct Extents {
         for (int j = 0; j < N_AUX; ++j) {
             amax[j] = max_nn(I.aux[j], amax[j]);
             amin[j] = min_nn(I.aux[j], amin[j]);
-            amean[j] = mean_time(amean[j], I.aux[j], dt, span);
+            amean[j] = mean_time(amean[j], I.aux[j], w);
         }
     }
     // per-step means (nhood1: observer_neighborhood_1.clh:250-261)
@@ -177,7 +189,7 @@ struct Observer {
         const realtype span = I.t - t_start;
         xmax = max_nn(I.x[F_VAR_IX], xmax);
         xmin = min_nn(I.x[F_VAR_IX], xmin);
-        xmean = mean_time(xmean, I.x[F_VAR_IX], dt, span);
+        xmean = mean_time(xmean, I.x[F_VAR_IX], mean_weight(dt, span));
         dxmax = max_nn(I.k1[F_VAR_IX], dxmax);
         dxmin = min_nn(I.k1[F_VAR_IX], dxmin);
     }
@@ -211,7 +223,7 @@ struct Observer {
         ++steps;
         const realtype dt = I.t - t_last;
         t_last = I.t;
-        ext.update_time(I, dt, I.t - t_start);
+        ext.update_time(I, mean_weight(dt, I.t - t_start));
     }
     __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
@@ -262,7 +274,7 @@ struct Observer {
         tb[0] = tb[1]; tb[1] = tb[2]; tb[2] = I.t;
         xf[0] = xf[1]; xf[1] = xf[2]; xf[2] = I.x[F_VAR_IX];
         d1 = d2; d2 = I.k1[F_VAR_IX];
-        ext.update_time(I, tb[2] - tb[1], I.t - t_start);
+        ext.update_time(I, mean_weight(tb[2] - tb[1], I.t - t_start));
         if (steps < 2) return;
         if (d1 < 0.0 && d2 > 0.0) { // local minimum between maxima (:269-282)
             realtype lowest;
@@ -499,7 +511,7 @@ struct Observer {
         df1 = df2; df2 = I.k1[F_VAR_IX];
         const realtype dt = tb[2] - tb[1];
         step_dt.push(dt, steps);
-        ext.update_time(I, dt, I.t - t_start);
+        ext.update_time(I, mean_weight(dt, I.t - t_start));
         if (steps < 2) return;
         if (found) {
             if (df1 >= 0.0 && df2 < 0.0) peaks++;
@@ -631,7 +643,7 @@ struct Observer {
         d1 = d2; d2 = I.k1[F_VAR_IX];
         const realtype dt = tb[2] - tb[1];
         step_dt.push(dt, steps);
-        ext.update_time(I, dt, I.t - t_start);
+        ext.update_time(I, mean_weight(dt, I.t - t_start));
         if (steps > 1) {
             if (d1 > 0.0 && d2 < 0.0) peaks++; // local maximum of the feature variable
             if (d1 < 0.0 && d2 > 0.0) {        // local minimum: remember its value
@@ -646,7 +658,7 @@ struct Observer {
                 }
             } else {
                 const realtype since = I.t - t_this_down;
-                if (since > 0.0) down_mean = mean_time(down_mean, I.x[F_VAR_IX], dt, since);
+                if (since > 0.0) down_mean = mean_time(down_mean, I.x[F_VAR_IX], mean_weight(dt, since));
             }
         }
     }
