@@ -209,7 +209,7 @@ def run_ours(args):
     prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"],
                        kernels=_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES,
                        work_queue=bool(args.work_queue), block_size=args.block, min_blocks_per_sm=args.min_blocks,
-                       staged_trajectory=bool(args.staged))
+                       staged_trajectory=bool(args.staged), observer_in_shared=bool(args.obs_smem))
     sim = _rt.Sim(prog, device=local)
     sim.set_solver_params(**w["solver"])
     sim.set_observer_params(**w["observer_params"])
@@ -374,6 +374,7 @@ def main():
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged", type=int, default=0, help="trajectory: shared-memory staged TMA bulk stores")
+    ap.add_argument("--obs-smem", type=int, default=0, help="features: observer state in shared memory")
     ap.add_argument("--shuffle", type=int, default=0, help="randomly permute the parameter grid (heterogeneous warps)")
     args = ap.parse_args()
     if args.impl == "reference":

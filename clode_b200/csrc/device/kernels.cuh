@@ -224,6 +224,47 @@ clode_transient()
 }
 
 #ifdef CLODE_WITH_FEATURES
+// Where the observer state lives while an instance is being integrated.
+//  default            : registers (best for the light observers: basic, basicall)
+//  CLODE_OBS_SMEM     : a per-thread slot in dynamic shared memory.  The observer is touched once per ACCEPTED
+//                       step, outside the RK stage evaluations, so shared-memory latency is irrelevant, while the
+//                       fat observers (thresh2 / nhood1 / nhood2 / localmax: 60-90 reals for nVar = 4) otherwise
+//                       push the kernel past 250 registers and into local-memory spills.  The slot size is an odd
+//                       number of 8-byte words, which makes the thread-strided (array-of-structs) accesses of a
+//                       warp bank-conflict free for the 64-bit fields.
+#ifdef CLODE_OBS_SMEM
+#define CLODE_OBS_SLOT_WORDS (((sizeof(Observer) + 7) / 8) | 1)
+extern __shared__ double clode_dynamic_smem[];
+CLODE_DEV Observer &observer_slot() { return *reinterpret_cast<Observer *>(clode_dynamic_smem + (size_t)threadIdx.x * CLODE_OBS_SLOT_WORDS); }
+#define CLODE_OBSERVER_MEMBER Observer &ob
+#define CLODE_OBSERVER_INIT , ob(observer_slot())
+// The per-step observer work as an out-of-line call on the shared-memory slot.  Inlined, the compiler
+// promotes the slot's fields back into registers for the whole time loop (no aliasing to stop it), which
+// defeats the purpose; behind a call boundary the observer's registers exist only inside the call.
+struct StepView {
+    realtype t, x[NV], k1[NV], aux[NA_];
+};
+static __device__ __noinline__ bool observe_step(Observer *ob, const StepView v)
+{
+    const ObserverParams op = observer_params(clode_args);
+    Instance J;
+    J.t = v.t;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { J.x[j] = v.x[j]; J.k1[j] = v.k1[j]; }
+#pragma unroll
+    for (int j = 0; j < NA_; ++j) J.aux[j] = v.aux[j];
+    ob->update(J, op);
+    bool terminal = false;
+    if (ob->event(J, op))
+        terminal = ob->on_event(J, op);
+    return terminal;
+}
+#else
+#define CLODE_OBS_SLOT_WORDS 0
+#define CLODE_OBSERVER_MEMBER Observer ob
+#define CLODE_OBSERVER_INIT
+#endif
+
 // ---- initializeObserver (clode/cpp/initializeObserver.cl:9-83) -------------------------------
 struct WarmupJob {
     const KernelArgs &a;
@@ -232,12 +273,12 @@ struct WarmupJob {
     Controller ctl;
     realtype t_end;
     Instance I;
-    Observer ob;
+    CLODE_OBSERVER_MEMBER;
     unsigned int step;
     realtype h;
     bool clean;
     __device__ __forceinline__ WarmupJob(const KernelArgs &a_)
-        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
     __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); ob.init(I); step = 0; h = I.dt; clean = true; }
     // strict '<' (initializeObserver.cl:62); one-pass observers do no warm-up integration at all
     __device__ __forceinline__ bool live() const { return CLODE_TWO_PASS && I.t < t_end && step < sp.max_steps; }
@@ -280,12 +321,12 @@ struct FeaturesJob {
     Controller ctl;
     realtype t_end;
     Instance I;
-    Observer ob;
+    CLODE_OBSERVER_MEMBER;
     unsigned int step;
     realtype h;
     bool clean, alive;
     __device__ __forceinline__ FeaturesJob(const KernelArgs &a_)
-        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
     __device__ __forceinline__ void begin(size_t i)
     {
         load_instance(I, a, i);
@@ -300,10 +341,20 @@ struct FeaturesJob {
         if (advance(I, h, clean, sp, ctl, t_end)) {
             ++step;
             // features.cl:71-81: update, then event test, then event features (a terminal event ends the run)
+#ifdef CLODE_OBS_SMEM
+            StepView v;
+            v.t = I.t;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { v.x[j] = I.x[j]; v.k1[j] = I.k1[j]; }
+#pragma unroll
+            for (int j = 0; j < NA_; ++j) v.aux[j] = I.aux[j];
+            const bool terminal = observe_step(&ob, v);
+#else
             ob.update(I, op);
             bool terminal = false;
             if (ob.event(I, op))
                 terminal = ob.on_event(I, op);
+#endif
             alive = !terminal && I.t <= t_end && step < sp.max_steps;
         }
     }
@@ -334,6 +385,7 @@ extern "C" __global__ void clode_observer_layout(int *out)
     out[0] = c.nreal;
     out[1] = c.nuint;
     out[2] = CLODE_TWO_PASS;
+    out[3] = (int)(CLODE_OBS_SLOT_WORDS * 8); // bytes of dynamic shared memory per thread (0: observer in registers)
 }
 #endif // CLODE_WITH_FEATURES
 

@@ -77,7 +77,7 @@ struct ProgramSpec {
     int n_var = 0, n_par = 0, n_aux = 0, n_wiener = 0;
     int f_var = 0, e_var = 0, n_store = 0;
     int kernels = CLODE_KERNEL_TRANSIENT;
-    bool bit_exact = false, work_queue = false, staged = false;
+    bool bit_exact = false, work_queue = false, staged = false, obs_smem = false;
     int block = 128, min_blocks = 4;
 };
 
@@ -102,6 +102,7 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
     s.work_queue = d->work_queue != 0;
     s.staged = d->staged_trajectory != 0;
+    s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
     s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4; // 0 = chosen at build time (clode_sim_build)
@@ -133,6 +134,7 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
+    if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
     return o;
 }
 
@@ -297,6 +299,7 @@ struct clode_sim {
     CUdeviceptr args_symbol = 0; // __constant__ KernelArgs clode_args
     CUfunction k_transient = nullptr, k_init = nullptr, k_features = nullptr, k_trajectory = nullptr, k_layout = nullptr;
     int od_nreal = 0, od_nuint = 0, two_pass = 0;
+    int obs_slot_bytes = 0; // dynamic shared memory per thread of the observer kernels
     int n_features = 0;
 
     size_t n = 0;
@@ -389,11 +392,16 @@ struct clode_sim {
         return a;
     }
 
+    size_t dynamic_smem(CUfunction f) const
+    {
+        return (f == k_features || f == k_init) ? (size_t)obs_slot_bytes * spec.block : 0;
+    }
+
     int grid_for(CUfunction f, unsigned &grid)
     {
         if (spec.work_queue) {
             int per_sm = 1;
-            CUresult r = d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, spec.block, 0);
+            CUresult r = d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, spec.block, dynamic_smem(f));
             if (r != CUDA_SUCCESS) return cu(r, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
             size_t want = (n + spec.block - 1) / spec.block;
             size_t persistent = (size_t)std::max(per_sm, 1) * sm_count;
@@ -433,7 +441,7 @@ struct clode_sim {
         // (pageable source: the driver stages the bytes before cuMemcpyHtoDAsync returns)
         if ((rc = cu(d->cuMemcpyHtoDAsync(args_symbol, &a, sizeof a, stream), "upload kernel arguments"))) return rc;
         if (first && (rc = cu(d->cuEventRecord(ev0, stream), "cuEventRecord"))) return rc;
-        if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, 0, stream, nullptr, nullptr), what))) return rc;
+        if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, (unsigned)dynamic_smem(f), stream, nullptr, nullptr), what))) return rc;
         ++launches;
         if (last) {
             if ((rc = cu(d->cuEventRecord(ev1, stream), "cuEventRecord"))) return rc;
@@ -732,15 +740,21 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
     if (spec.kernels & CLODE_KERNEL_FEATURES) {
         // ask the module how many observer-state rows it needs
         CUdeviceptr tmp = 0;
-        if ((rc = s->cu(s->d->cuMemAlloc(&tmp, 16), "cuMemAlloc"))) return rc;
+        if ((rc = s->cu(s->d->cuMemAlloc(&tmp, 32), "cuMemAlloc"))) return rc;
         void *params[] = {&tmp};
         rc = s->cu(s->d->cuLaunchKernel(s->k_layout, 1, 1, 1, 1, 1, 1, 0, s->stream, params, nullptr), "clode_observer_layout");
-        int host[3] = {0, 0, 0};
+        int host[4] = {0, 0, 0, 0};
         if (!rc) rc = s->cu(s->d->cuStreamSynchronize(s->stream), "clode_observer_layout");
         if (!rc) rc = s->cu(s->d->cuMemcpyDtoH(host, tmp, sizeof host), "cuMemcpyDtoH");
         s->d->cuMemFree(tmp);
         if (rc) return rc;
         s->od_nreal = host[0]; s->od_nuint = host[1]; s->two_pass = host[2];
+        s->obs_slot_bytes = host[3];
+        if (s->obs_slot_bytes > 0) {
+            const int bytes = s->obs_slot_bytes * spec.block;
+            if ((rc = s->cu(s->d->cuFuncSetAttribute(s->k_features, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes), "dynamic shared memory (features)"))) return rc;
+            if ((rc = s->cu(s->d->cuFuncSetAttribute(s->k_init, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, bytes), "dynamic shared memory (initializeObserver)"))) return rc;
+        }
     }
     s->n_features = observer_feature_count(spec.observer, spec.n_var, spec.n_aux, spec.n_store);
     s->real_size = spec.single ? 4 : 8;
@@ -1094,7 +1108,8 @@ int clode_sim_kernel_info(clode_sim *s, int kernel, clode_kernel_info *info)
     s->d->cuFuncGetAttribute(&info->const_bytes, CU_FUNC_ATTRIBUTE_CONST_SIZE_BYTES, f);
     s->d->cuFuncGetAttribute(&info->max_threads, CU_FUNC_ATTRIBUTE_MAX_THREADS_PER_BLOCK, f);
     info->block_size = s->spec.block;
-    s->d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&info->blocks_per_sm, f, s->spec.block, 0);
+    s->d->cuOccupancyMaxActiveBlocksPerMultiprocessor(&info->blocks_per_sm, f, s->spec.block, s->dynamic_smem(f));
+    info->shared_bytes += (int)s->dynamic_smem(f);
     unsigned grid = 0;
     if (s->n) s->grid_for(f, grid);
     info->grid_size = (int)grid;

@@ -87,6 +87,8 @@ typedef struct clode_program_desc {
     int min_blocks_per_sm;    /* __launch_bounds__ second argument; 0 = chosen by spill check            */
     int staged_trajectory;    /* 1: trajectory rows staged in shared memory and written by TMA bulk copies
                                  (fixed-step methods); 0: per-thread coalesced stores                     */
+    int observer_in_shared;   /* 1: observer state in a per-thread shared-memory slot instead of registers
+                                 (for the fat observers); 0: registers                                    */
 } clode_program_desc;
 
 /* compile only (no GPU needed): returns malloc'd cubin + log; caller frees with clode_free */

@@ -337,3 +337,31 @@ def test_cuda_staged_trajectory_bit_exact(rt, model, stepper, n, nout, max_store
             assert np.array_equal(r[k].reshape(rows, width, n)[m], o[k].reshape(rows, width, n)[m]), k
     assert_bit_equal(r, o, "staged trajectory", keys=["n_stored", "xf", "tf", "dt", "rng"])
     g.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# observer state kept in a shared-memory slot (out-of-line observer step) instead of registers
+@pytest.mark.parametrize("model,stepper,observer", [("lactotroph", "bs23", "thresh2"), ("lactotroph", "dopri5", "nhood2"),
+                                                    ("lorenz63", "dopri5", "localmax"), ("lactotroph", "rk4", "nhood1"),
+                                                    ("lorenz63", "bs23", "basicall")])
+def test_cuda_observer_in_shared_memory_bit_exact(rt, model, stepper, observer):
+    n = 333
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[1] / 4)
+    ns = 2 if observer in ("localmax", "nhood2", "thresh2") else 0
+    sp = Solver(dt=0.05 if stepper == "rk4" else 0.1, dtmax=10.0, abstol=1e-6, reltol=1e-4, max_steps=200000)
+    op = Observer(max_event_count=25, max_event_timestamps=ns, x_up_threshold=0.3, x_down_threshold=0.2, nhood_radius=0.1)
+    g = GpuRun(rt, model, stepper, observer, ns, bit_exact=True, obs_smem=True)
+    g.setup(ts, x0, pars, sp, op, seed=3)
+    r = g.features()
+    o = run_oracle(restate.OracleLib(Config(model, stepper, observer, ns, math="pm")), "features", ts, x0, pars, sp, op, seed=3)
+    assert_bit_equal(r, o, f"{model} {stepper} {observer} (observer in shared memory)")
+    # continuation: the slot is re-loaded from the SoA record at the start of the next call
+    g.sim.shift_x0()
+    g.sim.set_tspan(ts[1], ts[1] + (ts[1] - ts[0]))
+    r2 = g.features(initialize=0)
+    lib = restate.OracleLib(Config(model, stepper, observer, ns, math="pm"))
+    o1 = run_oracle(lib, "features", ts, x0, pars, sp, op, seed=3)
+    o2 = lib.features((ts[1], ts[1] + (ts[1] - ts[0])), o1["xf"], pars, sp, op, o1["dt"], o1["rng"], initialize=False)
+    assert_bit_equal(r2, o2, "continued")
+    g.close()

@@ -39,12 +39,12 @@ class GpuRun:
     """Drive the CUDA kernels through the C ABI (clode_b200._rt.Sim) with oracle-style arguments."""
 
     def __init__(self, rt, model, stepper, observer="basic", n_store=0, bit_exact=True, single=False,
-                 f_var=0, e_var=0, work_queue=False, block=0, staged=False):
+                 f_var=0, e_var=0, work_queue=False, block=0, staged=False, obs_smem=False):
         nv, npar, na, nw = MODELS[model]
         self.rt = rt
         self.prog = rt.Program(rhs_source(model), stepper, nv, npar, na, nw, observer=observer, bit_exact=bit_exact,
                                n_store_events=n_store, f_var_ix=f_var, e_var_ix=e_var, single_precision=single,
-                               work_queue=work_queue, block_size=block, staged_trajectory=staged)
+                               work_queue=work_queue, block_size=block, staged_trajectory=staged, observer_in_shared=obs_smem)
         self.sim = rt.Sim(self.prog)
         self.n_store = n_store
 
