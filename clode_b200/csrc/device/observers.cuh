@@ -25,7 +25,7 @@
 #endif
 #define NS_ (N_STORE_EVENTS > 0 ? N_STORE_EVENTS : 1)
 
-// struct ObserverParams — clode/cpp/observers.cl:25-46 (kernel argument, by value).
+// struct ObserverParams — clode/cpp/observers.cl:25-46 (rebuilt per thread from the constant argument block).
 // eVarIx / fVarIx are carried for completeness; the kernels use E_VAR_IX / F_VAR_IX.
 struct ObserverParams {
     unsigned int eVarIx, fVarIx, maxEventCount, maxEventTimestamps;

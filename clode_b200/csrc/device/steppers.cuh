@@ -32,7 +32,7 @@
 #define NA_ (N_AUX > 0 ? N_AUX : 1)
 #define NW_ (N_WIENER > 0 ? N_WIENER : 1)
 
-// struct SolverParams — clode/cpp/clODE_struct_defs.cl:11-20 (passed by value as a kernel argument)
+// struct SolverParams — clode/cpp/clODE_struct_defs.cl:11-20 (rebuilt per thread from the constant argument block)
 struct SolverParams {
     realtype dt, dtmax, abstol, reltol;
     unsigned int max_steps, max_store, nout;

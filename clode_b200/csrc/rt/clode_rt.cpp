@@ -15,7 +15,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
-#include <map>
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
@@ -850,6 +849,7 @@ int clode_sim_set_solver_params(clode_sim *s, const clode_solver_params *sp)
 {
     if (!s || !sp) return fail(CLODE_ERR_INVALID, "null argument");
     s->sp = *sp;
+    if (s->sp.nout == 0) s->sp.nout = 1; // `step % nout` (trajectory.cl:84) is undefined for 0; store every step instead
     return CLODE_OK;
 }
 
