@@ -209,7 +209,8 @@ def run_ours(args):
     prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"],
                        kernels=_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES,
                        work_queue=bool(args.work_queue), block_size=args.block, min_blocks_per_sm=args.min_blocks,
-                       staged_trajectory=bool(args.staged), observer_in_shared=bool(args.obs_smem))
+                       staged_trajectory=bool(args.staged), observer_in_shared=bool(args.obs_smem),
+                       single_precision=bool(args.single))
     sim = _rt.Sim(prog, device=local)
     sim.set_solver_params(**w["solver"])
     sim.set_observer_params(**w["observer_params"])
@@ -345,8 +346,9 @@ def run_ours(args):
     line = {
         "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": value, "unit": "instance-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "instances_per_gpu": n, "accepted_steps_per_pass": total_steps_per_pass,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.single else "f64",
+        "data": "synthetic",
+        "config": {"workload": w["desc"] if not args.single else w["desc"].replace("f64", "f32"), "instances_per_gpu": n, "accepted_steps_per_pass": total_steps_per_pass,
                    "l2": "inputs+outputs per pass exceed the 126 MB L2; the kernel is FP64-pipe bound, not memory bound",
                    "kernel": info, "work_queue": bool(args.work_queue), "wall_ms_per_step": wall_ms / args.steps},
         "clocks": clocks,
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--staged", type=int, default=0, help="trajectory: shared-memory staged TMA bulk stores")
     ap.add_argument("--obs-smem", type=int, default=0, help="features: observer state in shared memory")
+    ap.add_argument("--single", type=int, default=0, help="single precision (the reference's Python default); not the headline")
     ap.add_argument("--shuffle", type=int, default=0, help="randomly permute the parameter grid (heterogeneous warps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -43,8 +43,14 @@ struct SolverParams {
 // except possibly the sign of a zero result.  In SASS the library fmax on doubles is DSETP + FSEL +
 // SEL + LOP3 + moves (~7 issue slots, NaN quieting included); this form is DSETP + 2 SEL.  The step loop
 // evaluates ~20 of them per attempt.
+#if defined(CLODE_SINGLE_PRECISION)
+// FP32 has native min/max instructions (FMNMX) with exactly these NaN semantics
+CLODE_DEV realtype max_nn(const realtype v, const realtype m) { return fmaxf(v, m); }
+CLODE_DEV realtype min_nn(const realtype v, const realtype m) { return fminf(v, m); }
+#else
 CLODE_DEV realtype max_nn(const realtype v, const realtype m) { return v > m ? v : m; }
 CLODE_DEV realtype min_nn(const realtype v, const realtype m) { return v < m ? v : m; }
+#endif
 CLODE_DEV realtype clamp_nn(const realtype v, const realtype lo, const realtype hi) { return min_nn(max_nn(v, lo), hi); }
 
 // a / b for the engine's own bookkeeping divisions (error normalisation, running means).

@@ -175,3 +175,25 @@ def test_trajectory_store_limit_and_shapes(clode):
     assert len(res) == 70 and all(len(r.t) == 40 for r in res)
     assert np.allclose(res[3].t, np.arange(40) * 1.0)
     assert np.array_equal(np.asarray(sim._integrator.get_n_stored()), np.full(70, 40))
+
+
+def test_in_process_two_gpus(clode, rt):
+    """device_ids=[0, 1]: one runtime object per physical GPU, launches overlap, results identical to one GPU"""
+    if rt.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 20000
+    ts, x0, pars = ensemble("lorenz63", n)
+    kw = dict(src_file=model("lorenz63"), variables={"x": 1.0, "y": 1.0, "z": 1.0},
+              parameters={"r": 28.0, "s": 10.0, "b": 8.0 / 3.0}, aux=["dx"], single_precision=False,
+              stepper=clode.Stepper.dormand_prince, dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, t_span=(0.0, 30.0),
+              observer=clode.Observer.local_max, platform_id=0)
+    out = []
+    for ids in ([0], [0, 1], [1]):
+        fs = clode.FeatureSimulator(device_ids=ids, **kw)
+        fs.set_ensemble(parameters=pars.reshape(3, n).T.copy())
+        res = fs.features()
+        out.append((res.to_ndarray(), fs.get_final_state(), fs._integrator.get_last_kernel_ms()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0], out[2][0])
+    # two GPUs working concurrently: the slower shard takes clearly less than the whole job on one GPU
+    assert out[1][2] < 0.75 * out[0][2]
