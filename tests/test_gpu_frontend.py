@@ -181,7 +181,7 @@ def test_in_process_two_gpus(clode, rt):
     """device_ids=[0, 1]: one runtime object per physical GPU, launches overlap, results identical to one GPU"""
     if rt.device_count() < 2:
         pytest.skip("needs two GPUs")
-    n = 20000
+    n = 1 << 18  # enough blocks to fill two GPUs, so that the concurrency shows in the kernel time
     ts, x0, pars = ensemble("lorenz63", n)
     kw = dict(src_file=model("lorenz63"), variables={"x": 1.0, "y": 1.0, "z": 1.0},
               parameters={"r": 28.0, "s": 10.0, "b": 8.0 / 3.0}, aux=["dx"], single_precision=False,
