@@ -34,7 +34,6 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-sys.path.insert(0, os.path.join(REPO, "tests"))
 
 N_PER_GPU = 1 << 20
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: SMs x FP64 lanes x 2 x max clock
@@ -181,8 +180,7 @@ def run_ours(args):
     import torch
 
     from clode_b200 import _rt, build
-    from problems import rhs_source
-    from oracle.common import MODELS
+    from clode_b200.models import MODELS, rhs_source
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -18,16 +18,12 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MODELS_DIR = os.path.join(REPO, "clode_b200", "models")
 REFERENCE_ROOT = os.environ.get("CLODE_REFERENCE_ROOT", "/root/reference")
 
-# name -> (nVar, nPar, nAux, nWiener); files live in clode_b200/models/<name>.cl
-MODELS = {
-    "lorenz63": (3, 3, 1, 0),
-    "vanderpol": (2, 1, 0, 0),
-    "thompson_a1": (2, 4, 1, 0),
-    "lactotroph": (4, 3, 1, 0),
-    "lactotroph_noise": (4, 4, 1, 1),
-    "chay_keizer": (3, 3, 0, 0),
-    "sine_drive": (1, 1, 3, 0),
-}
+# model registry (dimensions + RHS files) lives with the product; the oracle only reads it
+import sys as _sys
+
+if REPO not in _sys.path:
+    _sys.path.insert(0, REPO)
+from clode_b200.models import MODELS  # noqa: E402  name -> (nVar, nPar, nAux, nWiener)
 
 # the reference's own RHS files for the same systems (only present in the build
 # container); used to check that clode_b200/models/*.cl are arithmetic-identical.

@@ -11,11 +11,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-from oracle.common import MODELS, MODELS_DIR  # noqa: E402
-
-
-def rhs_source(model: str) -> str:
-    return open(os.path.join(MODELS_DIR, model + ".cl")).read()
+from clode_b200.models import MODELS, MODELS_DIR, rhs_source  # noqa: E402,F401
 
 
 def ensemble(model: str, n: int):
