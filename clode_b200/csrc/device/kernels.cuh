@@ -124,7 +124,7 @@ CLODE_DEV void store_instance(const Instance &I, const KernelArgs &a, const size
 // advance by one ATTEMPT; true when an accepted (or abandoned, flag -1) step completed
 #if !CLODE_ADAPTIVE
 struct Controller {};
-CLODE_DEV Controller make_controller(const SolverParams &) { return Controller(); }
+CLODE_DEV Controller make_controller(const SolverParams &, realtype) { return Controller(); }
 #endif
 
 CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const Controller &ctl,
@@ -209,7 +209,7 @@ struct TransientJob {
     unsigned int step;
     realtype h;
     bool clean;
-    __device__ __forceinline__ TransientJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ TransientJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) {}
     __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); step = 0; h = I.dt; clean = true; }
     __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps; }
     __device__ __forceinline__ void attempt() { if (advance(I, h, clean, sp, ctl, t_end)) ++step; }
@@ -278,7 +278,7 @@ struct WarmupJob {
     realtype h;
     bool clean;
     __device__ __forceinline__ WarmupJob(const KernelArgs &a_)
-        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
     __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); ob.init(I); step = 0; h = I.dt; clean = true; }
     // strict '<' (initializeObserver.cl:62); one-pass observers do no warm-up integration at all
     __device__ __forceinline__ bool live() const { return CLODE_TWO_PASS && I.t < t_end && step < sp.max_steps; }
@@ -326,12 +326,13 @@ struct FeaturesJob {
     realtype h;
     bool clean, alive;
     __device__ __forceinline__ FeaturesJob(const KernelArgs &a_)
-        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
+        : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
     __device__ __forceinline__ void begin(size_t i)
     {
         load_instance(I, a, i);
         ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
         ob.visit(ld);
+        ob.open_means();
         step = 0; h = I.dt; clean = true;
         alive = I.t <= t_end && step < sp.max_steps;
     }
@@ -361,6 +362,7 @@ struct FeaturesJob {
     __device__ __forceinline__ void end(size_t i)
     {
         FeatureOut out = {(realtype *)a.F, (size_t)a.n, i, 0};
+        ob.close_means();
         ob.emit(out);
         ob.rebase(I.t - (realtype)a.t0);
         ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
@@ -424,7 +426,7 @@ struct TrajectoryJob {
     unsigned int step, row;
     realtype h;
     bool clean;
-    __device__ __forceinline__ TrajectoryJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp)), t_end((realtype)a_.t1) {}
+    __device__ __forceinline__ TrajectoryJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) {}
     __device__ __forceinline__ void begin(size_t i)
     {
         load_instance(I, a, i);

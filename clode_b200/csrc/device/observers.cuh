@@ -35,22 +35,33 @@ struct ObserverParams {
 // ---- small building blocks -----------------------------------------------------------
 
 // engine-internal forms of runningMeanTime / runningMean (clODE_utilities.cl:167-177).
-// Reference-arithmetic builds evaluate mean + (v - mean) * dt / span exactly as written.  In the production
-// build the weight w = dt / span is formed once per step (div_nr) and every running mean of that step is
-// updated with one FMA, mean + (v - mean) * w: the observers keep 1 (basic) to nVar + nAux + 1 (thresh2)
-// such means, and an FP64 division each was a fifth of the per-step observer cost.
-#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH) || defined(__CUDACC_EMU__)
+// Reference-arithmetic builds evaluate mean + (v - mean) * dt / span exactly as written, every step.
+//
+// Production build: the time-weighted means are carried as INTEGRALS while a kernel runs.  With
+// span_n = span_{n-1} + dt_n (true for every observer: dt is the time since the previous update, span the
+// time since t_start) the recurrence  m_n = m_{n-1} + (v_n - m_{n-1}) dt_n / span_n  is, multiplied by span_n,
+//     S_n = S_{n-1} + v_n dt_n,     S_n = m_n span_n,
+// so one FMA per mean per step replaces a subtraction, an FMA and the shared division (9 FP64 instructions per
+// step for `basic`).  open_means() converts the stored means on entry, S_0 = m_0 * (t_prev - t_start) — this also
+// reproduces what the recurrence does when a continued run restarts the clock — and close_means() divides
+// once before the features are emitted / the state is stored, so the persistent layout holds means in both tiers.
+#if CLODE_EXACT_ARITH
+#define CLODE_INTEGRAL_MEANS 0
 struct MeanWeight {
     realtype dt, span;
 };
 CLODE_DEV MeanWeight mean_weight(realtype dt, realtype span) { MeanWeight w = {dt, span}; return w; }
 CLODE_DEV realtype mean_time(realtype mean, realtype v, const MeanWeight &w) { return mean + (v - mean) * w.dt / w.span; }
+CLODE_DEV realtype mean_step(realtype mean, realtype v, realtype dt, realtype span) { return mean + (v - mean) * dt / span; }
 #else
+#define CLODE_INTEGRAL_MEANS 1
 struct MeanWeight {
-    realtype w;
+    realtype dt;
 };
-CLODE_DEV MeanWeight mean_weight(realtype dt, realtype span) { MeanWeight w = {div_nr(dt, span)}; return w; }
-CLODE_DEV realtype mean_time(realtype mean, realtype v, const MeanWeight &w) { return fma(v - mean, w.w, mean); }
+CLODE_DEV MeanWeight mean_weight(realtype dt, realtype) { MeanWeight w = {dt}; return w; }
+CLODE_DEV realtype mean_time(realtype sum, realtype v, const MeanWeight &w) { return fma(v, w.dt, sum); }
+// a running mean that is consumed while it runs (thresh2's down-state mean) keeps the recurrence
+CLODE_DEV realtype mean_step(realtype mean, realtype v, realtype dt, realtype span) { return fma(v - mean, div_nr(dt, span), mean); }
 #endif
 CLODE_DEV void mean_count(realtype *mean, realtype v, unsigned int count)
 {
@@ -121,6 +132,27 @@ struct Extents {
             amin[j] = min_nn(I.aux[j], amin[j]);
             amean[j] = mean_time(amean[j], I.aux[j], w);
         }
+    }
+    // mean <-> integral conversion of the time-weighted means (production build, see mean_time)
+    __device__ __forceinline__ void open_means(realtype span)
+    {
+#if CLODE_INTEGRAL_MEANS
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xmean[j] *= span;
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) amean[j] *= span;
+#endif
+    }
+    __device__ __forceinline__ void close_means(realtype span)
+    {
+#if CLODE_INTEGRAL_MEANS
+        if (span != ZERO) { // span == 0: nothing was ever accumulated (sums are 0, as the means were)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) xmean[j] /= span;
+#pragma unroll
+            for (int j = 0; j < N_AUX; ++j) amean[j] /= span;
+        }
+#endif
     }
     // per-step means (nhood1: observer_neighborhood_1.clh:250-261)
     __device__ __forceinline__ void update_count(const Instance &I, unsigned int count)
@@ -193,6 +225,19 @@ struct Observer {
         dxmax = max_nn(I.k1[F_VAR_IX], dxmax);
         dxmin = min_nn(I.k1[F_VAR_IX], dxmin);
     }
+    __device__ __forceinline__ void open_means()
+    {
+#if CLODE_INTEGRAL_MEANS
+        xmean *= t_last - t_start;
+#endif
+    }
+    __device__ __forceinline__ void close_means()
+    {
+#if CLODE_INTEGRAL_MEANS
+        const realtype span = t_last - t_start;
+        if (span != ZERO) xmean /= span;
+#endif
+    }
     __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ void emit(FeatureOut &o) const
@@ -225,6 +270,8 @@ struct Observer {
         t_last = I.t;
         ext.update_time(I, mean_weight(dt, I.t - t_start));
     }
+    __device__ __forceinline__ void open_means() { ext.open_means(t_last - t_start); }
+    __device__ __forceinline__ void close_means() { ext.close_means(t_last - t_start); }
     __device__ __forceinline__ bool event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ bool on_event(const Instance &, const ObserverParams &) { return false; }
     __device__ __forceinline__ void emit(FeatureOut &o) const
@@ -289,6 +336,8 @@ struct Observer {
             }
         }
     }
+    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); }
+    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); }
     __device__ __forceinline__ bool event(const Instance &, const ObserverParams &)
     {
         return steps >= 2 && d1 > 0.0 && d2 < 0.0;
@@ -401,6 +450,8 @@ struct Observer {
             }
         }
     }
+    __device__ __forceinline__ void open_means() {}  // per-step means only
+    __device__ __forceinline__ void close_means() {}
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2 || !found) return false;
@@ -524,6 +575,8 @@ struct Observer {
             for (int j = 0; j < NV; ++j) center[j] = I.x[j];
         }
     }
+    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); }
+    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); }
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2 || !found) return false;
@@ -658,10 +711,12 @@ struct Observer {
                 }
             } else {
                 const realtype since = I.t - t_this_down;
-                if (since > 0.0) down_mean = mean_time(down_mean, I.x[F_VAR_IX], mean_weight(dt, since));
+                if (since > 0.0) down_mean = mean_step(down_mean, I.x[F_VAR_IX], dt, since);
             }
         }
     }
+    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); }
+    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); }
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2) return false;

@@ -38,6 +38,15 @@ struct SolverParams {
     unsigned int max_steps, max_store, nout;
 };
 
+// Arithmetic tier.  1: every engine expression is evaluated as the reference writes it (bit-exact tier,
+// single precision, reference-math builds, the host emulation).  0: production double — same algorithm,
+// cheaper instruction sequences where noted (DESIGN.md §3 "instruction diet").
+#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH) || defined(__CUDACC_EMU__)
+#define CLODE_EXACT_ARITH 1
+#else
+#define CLODE_EXACT_ARITH 0
+#endif
+
 // fmax/fmin where the SECOND operand is known not to be NaN (a running extreme that started finite, a
 // solver parameter, ...).  Same value as fmax(v, m) / fmin(v, m) for every input — a NaN v yields m —
 // except possibly the sign of a zero result.  In SASS the library fmax on doubles is DSETP + FSEL +
@@ -53,13 +62,25 @@ CLODE_DEV realtype min_nn(const realtype v, const realtype m) { return v < m ? v
 #endif
 CLODE_DEV realtype clamp_nn(const realtype v, const realtype lo, const realtype hi) { return min_nn(max_nn(v, lo), hi); }
 
+#if CLODE_EXACT_ARITH
+CLODE_DEV realtype abs_nn(const realtype v) { return fabs(v); }
+CLODE_DEV realtype opaque(const realtype c) { return c; }
+#else
+// |v| on the bit pattern: one LOP3 on the integer pipe.  fabs() of a double that is then selected on
+// compiles to DADD -RZ,|v|, i.e. it occupies the FP64 pipe — the bottleneck of the step loop — for a move.
+CLODE_DEV double abs_nn(const double v) { return __hiloint2double(__double2hiint(v) & 0x7fffffff, __double2loint(v)); }
+// a constant the optimiser cannot see: `v > c ? v : c` with a literal c is rewritten into fmax(v, c), whose
+// double-precision expansion (DSETP.MAX + NaN quieting) costs 5 more issue slots than compare + select
+CLODE_DEV double opaque(const double c) { double r; asm("mov.f64 %0, %1;" : "=d"(r) : "d"(c)); return r; }
+#endif
+
 // a / b for the engine's own bookkeeping divisions (error normalisation, running means).
 // Reference-arithmetic builds: the IEEE division, as written in the reference.  Production double:
 // reciprocal by MUFU.RCP64H + two Newton steps, then one multiply — <= 2 ulp, no denormal / overflow
 // slow path (the divisors here are max(|x|, abstol/reltol) and elapsed times: normal, finite numbers).
 // libdevice's correctly-rounded division costs 8 FP64 + ~6 control instructions per call and a Lorenz
 // dopri5 attempt makes four of them.  The user's RHS keeps the IEEE `/`.
-#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH) || defined(__CUDACC_EMU__)
+#if CLODE_EXACT_ARITH
 CLODE_DEV realtype div_nr(const realtype a, const realtype b) { return a / b; }
 #else
 CLODE_DEV double div_nr(const double a, const double b)
@@ -257,6 +278,7 @@ CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, re
 struct Controller {
     realtype reltol, floor_;
     realtype scale; // 0.8 * reltol^(1/(p+1))   (production double only)
+    int floor_hi_min; // step_floor's exponent-field form applies to hi(t) in [floor_hi_min, 0x7ff00000): empty unless t_end > 0
 };
 #if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH)
 #define CLODE_EXACT_CONTROLLER 1
@@ -268,7 +290,10 @@ CLODE_DEV realtype controller_factor(const Controller &c, realtype nerr)
 #define CLODE_EXACT_CONTROLLER 0
 CLODE_DEV double controller_factor(const Controller &c, double nerr)
 {
-    const double x = fmin(fmax(nerr, 1e-30), 1e30);
+    // clamp to about [1e-30, 1e30] on the high word (nerr is >= 0 and never NaN: integer order == value order);
+    // any value out there saturates the [MAX_SHRINK, 5] clamp that follows, so the low word may stay
+    const int hi = min(max(__double2hiint(nerr), 0x39b4484b), 0x46293e59);
+    const double x = __hiloint2double(hi, __double2loint(nerr));
 #if defined(EXPLICIT_BS23)
     return c.scale * rcbrt(x);
 #else
@@ -284,23 +309,34 @@ CLODE_DEV double controller_factor(const Controller &c, double nerr)
 }
 #endif
 
-CLODE_DEV Controller make_controller(const SolverParams &sp)
+CLODE_DEV Controller make_controller(const SolverParams &sp, const realtype t_end)
 {
     Controller c;
     c.reltol = sp.reltol;
     c.floor_ = sp.abstol / sp.reltol;
     c.scale = RCONST(0.8) * pow(sp.reltol, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
+    c.floor_hi_min = t_end > ZERO ? (49 << 20) : 0x7ff00000;
     return c;
 }
 
 // hmin = 16 * | |nextafter(t, 1.1 t_end)| - t |   (adaptive_explicit_step.clh:17; "16 eps(t)")
 // nextafter written out on the bit pattern: same result as the library call for every non-NaN
 // input, without its NaN / signalling paths (about a third of the instructions).
-CLODE_DEV realtype step_floor(const realtype t, const realtype t_end)
+CLODE_DEV realtype step_floor(const realtype t, const realtype t_end, const int fast_hi_min)
 {
 #if defined(CLODE_SINGLE_PRECISION)
     return RCONST(16.0) * fabs(fabs(nextafter(t, RCONST(1.1) * t_end)) - t);
 #else
+#if !CLODE_EXACT_ARITH
+    // Common case: 0 < t <= t_end (every caller steps only while t <= t_end), t normal and >= 2^-974.
+    // nextafter then moves one ulp up, so the result is 16 ulp(t) = 2^(E-1071) exactly (E = biased exponent
+    // of t): built from the exponent field, no FP64-pipe instruction.  tests/test_pm_math.py pins the identity.
+    {
+        const int hi = __double2hiint(t);
+        if (hi >= fast_hi_min && hi < 0x7ff00000)
+            return __hiloint2double((hi & 0x7ff00000) - (48 << 20), 0);
+    }
+#endif
     const double target = 1.1 * t_end;
     long long bits = __double_as_longlong(t);
     double next;
@@ -324,18 +360,18 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
                                  const realtype t_end)
 {
     const realtype floor_ = ctl.floor_;
-    const realtype hmin = step_floor(I.t, t_end);
+    const realtype hmin = step_floor(I.t, t_end, ctl.floor_hi_min);
     realtype t1, xn[NV], kn[NV], err[NV];
 
     h = clamp_nn(h, hmin, sp.dtmax);
     h = trial_step(I, h, t1, xn, kn, err);
 
-    realtype nerr = ZERO;
+    realtype nerr = opaque(ZERO);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         // fmax(fmax(|x|, |xn|), floor) and norm_inf's fmax(|e|, running), NaN operands ignored as in the reference
-        err[j] = div_nr(err[j], max_nn(fabs(I.x[j]), max_nn(fabs(xn[j]), floor_)));
-        nerr = max_nn(fabs(err[j]), nerr);
+        err[j] = div_nr(err[j], max_nn(abs_nn(I.x[j]), max_nn(abs_nn(xn[j]), floor_)));
+        nerr = max_nn(abs_nn(err[j]), nerr);
     }
     const bool reject = nerr > sp.reltol;
     if (reject && h <= hmin) { // cannot shrink further: stepper() returns -1, state untouched
@@ -348,12 +384,12 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     if (clean)
         factor = controller_factor(ctl, nerr);
     if (reject) {
-        h *= clean ? max_nn(factor, MAX_SHRINK) : RCONST(0.5);
+        h *= clean ? max_nn(factor, opaque(MAX_SHRINK)) : RCONST(0.5);
         clean = false;
         return false;
     }
     if (clean)
-        h *= min_nn(factor, RCONST(5.0));
+        h *= min_nn(factor, opaque(RCONST(5.0)));
     h = min_nn(t_end - t1, h); // fmin(h, t_end - t1): h is never NaN here
     h = clamp_nn(h, hmin, sp.dtmax);
     I.dt = h;

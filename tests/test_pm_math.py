@@ -82,3 +82,24 @@ def test_special_values(pm):
     assert p(inf, 0.2) == inf and p(0.0, 0.2) == 0.0 and p(0.0, -1.0) == inf
     assert p(-2.0, 3.0) == pytest.approx(-8.0) and p(-2.0, 2.0) == pytest.approx(4.0) and np.isnan(p(-2.0, 0.5))
     assert p(4.0, 0.5) == pytest.approx(2.0, rel=1e-15) and p(2.0, 10.0) == pytest.approx(1024.0, rel=1e-15)
+
+
+def test_step_floor_exponent_identity():
+    """steppers.cuh step_floor(), production build: for 0 < t <= t_end, t normal and >= 2^-974,
+    16*| |nextafter(t, 1.1 t_end)| - t |  (adaptive_explicit_step.clh:17) == 2^(E-1071), E = biased exponent of t,
+    built as hi' = (hi & 0x7ff00000) - (48 << 20), lo' = 0."""
+    rng = np.random.default_rng(7)
+    t = np.concatenate([
+        np.exp(rng.uniform(np.log(2.0 ** -974), np.log(1e300), 20000)),
+        2.0 ** rng.integers(-974, 1000, 2000).astype(np.float64),          # exact powers of two
+        np.nextafter(2.0 ** rng.integers(-973, 1000, 2000).astype(np.float64), 0.0),  # all-ones mantissas
+        [2.0 ** -974, 1e-3, 0.01, 100.0, 1e4],
+    ])
+    t_end = t * np.concatenate([rng.uniform(1.0, 3.0, t.size - 5), [1.0, 1.0, 1.0, 1.0, 1.0]])
+    t_end = np.maximum(t_end, t)
+    want = 16.0 * np.abs(np.abs(np.nextafter(t, 1.1 * t_end)) - t)
+    bits = t.view(np.uint64)
+    hi = (bits >> np.uint64(32)).astype(np.int64)
+    assert np.all((hi >= (49 << 20)) & (hi < 0x7FF00000))
+    got = (((hi & 0x7FF00000) - (48 << 20)).astype(np.uint64) << np.uint64(32)).view(np.float64)
+    assert np.array_equal(got, want)
