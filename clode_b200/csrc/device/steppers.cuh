@@ -272,8 +272,8 @@ CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, re
 // chain, plus an IEEE division for its argument — a third of a Lorenz dopri5 step — for a factor
 // that is immediately clamped to [MAX_SHRINK, 5].  There the factor is computed division-free as
 //     0.8 * reltol^(1/(p+1)) * err^(-1/(p+1)),
-// the first two terms once per kernel, the last by Newton's iteration on z^-(p+1) = err seeded from
-// the SFU (FP32 lg2/ex2): ~14 FP64 instructions, <= 4 ulp, well inside OpenCL C's 16-ulp bound
+// the first two terms once per kernel, the last as an SFU seed (FP32 lg2/ex2) times one third-order
+// series correction: 8-9 FP64 instructions on a short chain, <= 2 ulp, well inside OpenCL C's 16-ulp bound
 // for pow.  err outside [1e-30, 1e30] saturates, which the clamps make indistinguishable.
 struct Controller {
     realtype reltol, floor_;
@@ -294,18 +294,19 @@ CLODE_DEV double controller_factor(const Controller &c, double nerr)
     // any value out there saturates the [MAX_SHRINK, 5] clamp that follows, so the low word may stay
     const int hi = min(max(__double2hiint(nerr), 0x39b4484b), 0x46293e59);
     const double x = __hiloint2double(hi, __double2loint(nerr));
+    // seed z ~ x^(-1/q) from the SFU (relative error < 1e-5), then ONE third-order correction: with
+    // d = x z^q - 1 the exact root is z (1 + d)^(-1/q), expanded to d^3 (|d| < 5e-5: truncation < 1e-18)
 #if defined(EXPLICIT_BS23)
-    return c.scale * rcbrt(x);
+    double z = (double)exp2f(-0.33333334f * __log2f((float)x));
+    const double d = fma(x, z * z * z, -1.0);
+    z = fma(z, d * fma(d, fma(d, -14.0 / 81.0, 2.0 / 9.0), -1.0 / 3.0), z); // (1+d)^(-1/3) = 1 - d/3 + 2/9 d^2 - 14/81 d^3
 #else
-    double z = (double)exp2f(-0.2f * __log2f((float)x)); // ~ x^(-1/5), relative error ~1e-6
-    const double fifth_x = -0.2 * x;
-    // Newton on f(z) = z^-5 - x :  z <- z (1.2 - 0.2 x z^5), twice: 1e-6 -> 1e-11 -> rounding level
-    double z2 = z * z;
-    z = z * fma(fifth_x, z2 * z2 * z, 1.2);
-    z2 = z * z;
-    z = z * fma(fifth_x, z2 * z2 * z, 1.2);
-    return c.scale * z;
+    double z = (double)exp2f(-0.2f * __log2f((float)x));
+    const double z2 = z * z;
+    const double d = fma(x, z2 * z2 * z, -1.0);
+    z = fma(z, d * fma(d, fma(d, -11.0 / 125.0, 3.0 / 25.0), -0.2), z); // (1+d)^(-1/5) = 1 - d/5 + 3/25 d^2 - 11/125 d^3
 #endif
+    return c.scale * z;
 }
 #endif
 
