@@ -299,6 +299,44 @@ def run_ours(args):
     h2d = 8 * n * (nv + npar + 1)
     d2h = 8 * n * nfeat
 
+    # ---- trajectory only: bringing the stored points themselves to the host -------
+    fetch = None
+    if is_traj and args.stream_rows > 0:
+        rows = w["solver"]["max_store"]
+        sizes = dict(t=rows * n, x=rows * n * nv, dx=rows * n * nv, aux=rows * n * na)
+        host = {k: _rt.pinned_empty(v, device=local) for k, v in sizes.items() if v}
+        which = dict(t=_rt.BUF_T, x=_rt.BUF_X, dx=_rt.BUF_DX, aux=_rt.BUF_AUX)
+
+        def single_launch_then_copy():
+            sim.set_dt(dt0)
+            sim.trajectory()
+            for k, a in host.items():
+                sim.get(which[k], a.size, out=a)
+
+        def streamed():
+            sim.set_dt(dt0)
+            sim.trajectory_stream(args.stream_rows, out=host, want=tuple(host))
+
+        times = {}
+        for name, fn in (("single_launch_then_copy", single_launch_then_copy), ("streamed", streamed)):
+            fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                fn()
+            barrier()
+            times[name] = (time.perf_counter() - t0) / args.steps
+            check = float(host["x"].reshape(rows, nv, n)[rows // 2].sum())
+            times[name + "_checksum"] = check
+        nbytes = 8 * sum(sizes.values())
+        fetch = {"rows": rows, "host_bytes": nbytes, "chunk_rows": args.stream_rows,
+                 "single_launch_then_copy_s": times["single_launch_then_copy"], "streamed_s": times["streamed"],
+                 "single_launch_then_copy_GBps": nbytes / times["single_launch_then_copy"] / 1e9,
+                 "streamed_GBps": nbytes / times["streamed"] / 1e9,
+                 "device_bytes_single_launch": 8 * (rows + 1) * n * (1 + 2 * nv + na),
+                 "device_bytes_streamed": 2 * 8 * min(args.stream_rows, rows + 1) * n * (1 + 2 * nv + na),
+                 "same_result": times["single_launch_then_copy_checksum"] == times["streamed_checksum"]}
+
     # ---- reduce over ranks -----------------------------------------------------------------------
     stats = torch.tensor([dev_ms, wall_ms, e2e_s, float(steps_per_pass), float(launches)], dtype=torch.float64, device="cuda")
     if dist:
@@ -321,7 +359,7 @@ def run_ours(args):
     info = sim.kernel_info(_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
     # (profiles/r01_*_summary.txt); None for workloads that were not captured
-    ncu_traffic = {"C2": 144.456192e6 + 121.891584e6, "C5": 21.757184e6 + 29.332668e9, "C5e": 18.968832e6 + 29.331877e9}
+    ncu_traffic = {"C2": 143.456768e6 + 122.234880e6, "C5": 21.757184e6 + 29.332668e9, "C5e": 18.968832e6 + 29.331877e9}
     traffic = ncu_traffic.get(args.workload) if n == default_n else None
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
@@ -356,6 +394,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": base,
     }
+    if fetch:
+        line["trajectory_fetch"] = fetch
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -373,6 +413,8 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stream-rows", type=int, default=0,
+                    help="trajectory workloads: also time fetching all stored points, single launch + copy vs streamed in chunks of this many rows")
     ap.add_argument("--staged", type=int, default=0, help="trajectory: shared-memory staged TMA bulk stores")
     ap.add_argument("--obs-smem", type=int, default=0, help="features: observer state in shared memory")
     ap.add_argument("--single", type=int, default=0, help="single precision (the reference's Python default); not the headline")

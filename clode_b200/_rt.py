@@ -137,6 +137,42 @@ class Program:
                            int(self.staged_trajectory), int(self.observer_in_shared))
 
 
+class _PinnedBlock:
+    """a clode_host_alloc block, freed with the last array that views it"""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib().clode_host_free(ctypes.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+class PinnedArray(np.ndarray):
+    """ndarray over page-locked host memory; `_block` (reached through .base by every view) owns the memory"""
+    _block = None
+
+
+def pinned_empty(count: int, device: int = 0) -> np.ndarray:
+    """flat float64 array in page-locked host memory (clode_host_alloc): device<->host copies run at the full
+    PCIe rate and, for the streamed trajectory, overlap the integration"""
+    count = int(count)
+    f = lib().clode_host_alloc
+    f.restype = ctypes.c_void_p
+    f.argtypes = [ctypes.c_int, ctypes.c_size_t]
+    lib().clode_host_free.argtypes = [ctypes.c_void_p]
+    lib().clode_host_free.restype = None
+    ptr = f(device, max(count, 1) * 8)
+    if not ptr:
+        raise RtError(-1, lib().clode_last_error().decode(errors="replace"))
+    buf = (ctypes.c_double * max(count, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=np.float64, count=count).view(PinnedArray)
+    arr._block = _PinnedBlock(ptr)
+    return arr
+
+
 def compile_program(prog: Program) -> tuple[bytes, str]:
     """NVRTC-compile to an sm_100a cubin; needs no GPU."""
     d = prog.c()
@@ -293,6 +329,31 @@ class Sim:
         _check(self._lib.clode_sim_get_n_stored(self._h, nst.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n)))
         return dict(t=self.get(BUF_T, rows * n), x=self.get(BUF_X, rows * n * nv), dx=self.get(BUF_DX, rows * n * nv),
                     aux=self.get(BUF_AUX, rows * n * na) if na else np.zeros(1), n_stored=nst, rows=rows)
+
+    def trajectory_stream(self, chunk_rows: int, out: dict | None = None, pinned: bool = False, want=("t", "x", "dx", "aux")):
+        """clode_sim_trajectory_stream: integrate in chunks of `chunk_rows` stored points, copying each chunk to
+        the host while the next one integrates.  Returns dict(t, x, dx, aux, n_stored, rows) with rows = max_store
+        (the rows the reference API returns).  `out` may hold preallocated flat float64 arrays (e.g. from
+        pinned_empty); outputs not listed in `want` are skipped."""
+        rows = self._sp.max_store
+        nv, na, n = self.prog.n_var, self.prog.n_aux, self.n
+        sizes = dict(t=rows * n, x=rows * n * nv, dx=rows * n * nv, aux=rows * n * na)
+        res, ptr = {}, {}
+        for k, size in sizes.items():
+            if k not in want or size == 0:
+                res[k], ptr[k] = (np.zeros(1) if k == "aux" else None), None
+                continue
+            a = out.get(k) if out else None
+            if a is None:
+                a = pinned_empty(size, device=0) if pinned else np.zeros(size, np.float64)
+            elif a.dtype != np.float64 or a.size != size or not a.flags.c_contiguous:
+                raise ValueError(f"out[{k!r}] must be a C-contiguous float64 array of {size} elements")
+            res[k], ptr[k] = a, a.ctypes.data_as(ctypes.c_void_p)
+        nst = np.empty(n, np.int32)
+        _check(self._lib.clode_sim_trajectory_stream(self._h, ctypes.c_size_t(chunk_rows), ptr["t"], ptr["x"], ptr["dx"],
+                                                     ptr["aux"], nst.ctypes.data_as(ctypes.c_void_p)))
+        res.update(n_stored=nst, rows=rows)
+        return res
 
     def get_trajectory_counts(self):
         nst = np.empty(self.n, np.int32)

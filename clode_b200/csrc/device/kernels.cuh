@@ -54,6 +54,12 @@ struct KernelArgs {
     void *tr_t, *tr_x, *tr_dx, *tr_aux; // [rows][n], [rows][N_VAR][n], [rows][N_VAR][n], [rows][N_AUX][n]
     int *n_stored;                 // [n]
     unsigned long long *queue;     // work-queue head (CLODE_WORK_QUEUE)
+    // chunked ("streamed") trajectory: one launch stores global rows [row_begin, row_end) into buffers that hold
+    // only those rows; the per-instance state needed to resume travels in xf/tf/dt/rng plus the two arrays below
+    void *rs_real;                 // [1 + N_WIENER][n]: cached normal variate, noise values of the next step
+    unsigned int *rs_uint;         // [3][n]: accepted steps so far, rows stored so far, variate cached?
+    unsigned int *chunk_flags;     // [2]: an instance is still live after this launch / highest row index stored
+    unsigned int row_begin, row_end, resume; // monolithic launch: 0, 0xffffffff, 0
 };
 
 extern "C" __constant__ KernelArgs clode_args;
@@ -416,6 +422,55 @@ CLODE_DEV void store_point(const Instance &I, const KernelArgs &a, const size_t 
 #endif
 }
 
+// state of a chunked trajectory between two launches: x, t, dt and the RNG words are where store_instance puts
+// them; the polar method's cached variate, the noise already drawn for the next step and the two counters go to
+// rs_real / rs_uint.  The slope and the aux variables are recomputed (same inputs, same getRHS).
+CLODE_DEV void suspend_instance(const Instance &I, const KernelArgs &a, const size_t i, const unsigned int step,
+                                const unsigned int row, const bool unfinished)
+{
+    const size_t n = a.n;
+    realtype *rr = (realtype *)a.rs_real;
+    rr[i] = I.rng.spare;
+#pragma unroll
+    for (int j = 0; j < N_WIENER; ++j)
+        rr[(size_t)(1 + j) * n + i] = I.w[j];
+    a.rs_uint[i] = step;
+    a.rs_uint[n + i] = row;
+    a.rs_uint[2 * n + i] = I.rng.have_spare ? 1u : 0u;
+    if (unfinished) a.chunk_flags[0] = 1u; // benign race: every writer stores the same value
+    if (row >= a.row_begin) atomicMax(a.chunk_flags + 1, row);
+}
+
+CLODE_DEV void resume_instance(Instance &I, const KernelArgs &a, const size_t i, unsigned int &step, unsigned int &row)
+{
+    const size_t n = a.n;
+    const realtype *xf = (const realtype *)a.xf, *pars = (const realtype *)a.pars, *rr = (const realtype *)a.rs_real;
+    I.t = ((const realtype *)a.tf)[i];
+    I.dt = ((const realtype *)a.dt)[i];
+#pragma unroll
+    for (int j = 0; j < N_PAR; ++j)
+        I.p[j] = __ldg(pars + (size_t)j * n + i);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        I.x[j] = xf[(size_t)j * n + i];
+    I.rng.s0 = a.rng[i];
+    I.rng.s1 = a.rng[n + i];
+    I.rng.have_spare = a.rs_uint[2 * n + i] != 0u;
+    I.rng.spare = rr[i];
+#pragma unroll
+    for (int j = 0; j < NA_; ++j)
+        I.aux[j] = ZERO;
+#pragma unroll
+    for (int j = 0; j < NW_; ++j)
+        I.w[j] = ZERO;
+#pragma unroll
+    for (int j = 0; j < N_WIENER; ++j)
+        I.w[j] = rr[(size_t)(1 + j) * n + i];
+    step = a.rs_uint[i];
+    row = a.rs_uint[n + i];
+    getRHS(I.t, I.x, I.p, I.k1, I.aux, I.w);
+}
+
 struct TrajectoryJob {
     const KernelArgs &a;
     SolverParams sp;
@@ -429,18 +484,26 @@ struct TrajectoryJob {
     __device__ __forceinline__ TrajectoryJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) {}
     __device__ __forceinline__ void begin(size_t i)
     {
-        load_instance(I, a, i);
-        inst = i; step = 0; row = 0; h = I.dt; clean = true;
-        store_point(I, a, i, 0);
+        inst = i; clean = true;
+        if (!a.resume) {
+            load_instance(I, a, i);
+            step = 0; row = 0;
+            store_point(I, a, i, 0);
+        } else {
+            resume_instance(I, a, i, step, row);
+        }
+        h = I.dt;
     }
-    __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps && row < sp.max_store; }
+    // trajectory.cl:76; `row + 1 < row_end`: the next point still belongs to this launch's rows
+    __device__ __forceinline__ bool unfinished() const { return I.t <= t_end && step < sp.max_steps && row < sp.max_store; }
+    __device__ __forceinline__ bool live() const { return unfinished() && row + 1 < a.row_end; }
     __device__ __forceinline__ void attempt()
     {
         if (advance(I, h, clean, sp, ctl, t_end)) {
             ++step;
             if (step % sp.nout == 0) {
                 ++row;
-                store_point(I, a, inst, row);
+                store_point(I, a, inst, row - a.row_begin);
             }
         }
     }
@@ -448,6 +511,7 @@ struct TrajectoryJob {
     {
         a.n_stored[i] = (int)row;
         store_instance(I, a, i, step);
+        if (a.rs_uint) suspend_instance(I, a, i, step, row, unfinished());
     }
 };
 

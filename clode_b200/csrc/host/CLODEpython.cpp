@@ -292,5 +292,7 @@ PYBIND11_MODULE(clode_cpp_wrapper, m)
         .def("get_t_array", [](CLODEtrajectory &c) { return to_array(c.getT()); })
         .def("get_x_array", [](CLODEtrajectory &c) { return to_array(c.getX()); })
         .def("get_dx_array", [](CLODEtrajectory &c) { return to_array(c.getDx()); })
-        .def("get_aux_array", [](CLODEtrajectory &c) { return to_array(c.getAux()); });
+        .def("get_aux_array", [](CLODEtrajectory &c) { return to_array(c.getAux()); })
+        .def("set_stream_chunk", &CLODEtrajectory::setStreamChunk, py::arg("rows"))
+        .def("get_stream_chunk", &CLODEtrajectory::getStreamChunk);
 }

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <future>
 #include <string>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -264,6 +265,8 @@ struct KernelArgs {
     double op_min_x_amp, op_min_imi, op_nhood_radius, op_x_up, op_x_down, op_dx_up, op_dx_down, op_eps_dx;
     unsigned long long n;
     CUdeviceptr x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
+    CUdeviceptr rs_real, rs_uint, chunk_flags;
+    unsigned int row_begin, row_end, resume;
 };
 
 std::string cu_error(DriverApi *d, CUresult r)
@@ -305,6 +308,10 @@ struct clode_sim {
     size_t real_size = 8;
     Buffer x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
     size_t tr_rows = 0; // allocated trajectory rows (max_store + 1)
+    // streamed trajectory: two chunk buffer sets (one integrates while the other is copied out) + resume state
+    struct Chunk { Buffer t, x, dx, aux; } chunk[2];
+    Buffer rs_real, rs_uint, chunk_flags;
+    unsigned int *flags_host = nullptr; // pinned, 2 words
     bool observer_initialized = false;
 
     double t0 = 0.0, t1 = 0.0;
@@ -367,7 +374,9 @@ struct clode_sim {
 
     void free_ensemble()
     {
-        Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue};
+        Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue,
+                         &chunk[0].t, &chunk[0].x, &chunk[0].dx, &chunk[0].aux, &chunk[1].t, &chunk[1].x, &chunk[1].dx, &chunk[1].aux,
+                         &rs_real, &rs_uint, &chunk_flags};
         for (Buffer *b : all) release(*b);
         n = 0; tr_rows = 0; observer_initialized = false;
     }
@@ -388,6 +397,7 @@ struct clode_sim {
         a.steps = steps.ptr; a.od_real = od_real.ptr; a.od_uint = od_uint.ptr; a.F = F.ptr;
         a.tr_t = tr_t.ptr; a.tr_x = tr_x.ptr; a.tr_dx = tr_dx.ptr; a.tr_aux = tr_aux.ptr;
         a.n_stored = n_stored.ptr; a.queue = queue.ptr;
+        a.row_begin = 0; a.row_end = 0xffffffffu; a.resume = 0; // one launch stores every row
         return a;
     }
 
@@ -427,13 +437,17 @@ struct clode_sim {
 
     int launch(CUfunction f, const char *what, bool first, bool last, bool blocking = true)
     {
+        return launch_with(f, args(), what, first, last, blocking);
+    }
+
+    int launch_with(CUfunction f, const KernelArgs &a, const char *what, bool first, bool last, bool blocking = true)
+    {
         if (!f) return fail(CLODE_ERR_STATE, std::string(what) + ": kernel not built");
         if (n == 0) return fail(CLODE_ERR_STATE, std::string(what) + ": no problem data set (nPts == 0)");
         int rc;
         if (spec.work_queue) {
             if ((rc = cu(d->cuMemsetD8Async(queue.ptr, 0, 8, stream), "reset work queue"))) return rc;
         }
-        KernelArgs a = args();
         unsigned grid = 1;
         if ((rc = grid_for(f, grid))) return rc;
         // arguments go to the module's __constant__ block, ordered in-stream before the launch
@@ -647,6 +661,7 @@ int clode_sim_destroy(clode_sim *s)
         s->d->cuStreamSynchronize(s->stream);
         s->free_ensemble();
         if (s->module) s->d->cuModuleUnload(s->module);
+        if (s->flags_host) s->d->cuMemFreeHost(s->flags_host);
         if (s->ev0) s->d->cuEventDestroy(s->ev0);
         if (s->ev1) s->d->cuEventDestroy(s->ev1);
         if (s->stream) s->d->cuStreamDestroy(s->stream);
@@ -980,6 +995,133 @@ static int run_trajectory(clode_sim *s, bool blocking)
         s->tr_rows = rows;
     }
     return s->launch(s->k_trajectory, "clode_trajectory", true, true, blocking);
+}
+
+// ---- streamed trajectory ------------------------------------------------------------------
+// The reference allocates nPts * max_store * (1 + 2 nVar + nAux) reals on the device in one piece and copies
+// them out after the kernel (CLODEtrajectory.cpp:45-95, 132-205; its own TODO at :47 and trajectory.py:166).
+// Here the run is cut into launches of `chunk_rows` stored points: the device holds two chunk buffers, and
+// while chunk k+1 integrates, a helper thread copies chunk k into the caller's full-size host arrays.
+// Between launches an instance lives in xf / tf / dt / rng + rs_real / rs_uint (kernels.cuh suspend_instance).
+namespace {
+struct HostOut { double *t, *x, *dx, *aux; };
+
+// copy rows [row0, row0 + rows) of one chunk to the host arrays (runs on the helper thread)
+int copy_chunk_out(clode_sim *s, int b, size_t row0, size_t rows, HostOut out)
+{
+    clode_sim::Scope scope(s);
+    const size_t n = s->n, nv = s->spec.n_var, na = s->spec.n_aux;
+    struct Part { double *dst; CUdeviceptr src; size_t width; } parts[] = {
+        {out.t, s->chunk[b].t.ptr, 1}, {out.x, s->chunk[b].x.ptr, nv}, {out.dx, s->chunk[b].dx.ptr, nv}, {out.aux, s->chunk[b].aux.ptr, na}};
+    std::vector<float> narrow;
+    for (const Part &p : parts) {
+        if (!p.dst || p.width == 0) continue;
+        const size_t count = rows * p.width * n;
+        double *dst = p.dst + row0 * p.width * n;
+        if (s->real_size == 8) {
+            int rc = s->cu(s->d->cuMemcpyDtoH(dst, p.src, count * 8), "trajectory_stream: copy to host");
+            if (rc) return rc;
+        } else {
+            narrow.resize(count);
+            int rc = s->cu(s->d->cuMemcpyDtoH(narrow.data(), p.src, count * 4), "trajectory_stream: copy to host");
+            if (rc) return rc;
+            for (size_t k = 0; k < count; ++k) dst[k] = (double)narrow[k];
+        }
+    }
+    return CLODE_OK;
+}
+} // namespace
+
+int clode_sim_trajectory_stream(clode_sim *s, size_t chunk_rows, double *t, double *x, double *dx, double *aux, int *n_stored)
+{
+    if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
+    if (!s->built || !s->k_trajectory) return fail(CLODE_ERR_STATE, "trajectory_stream: trajectory kernel not built");
+    if (s->n == 0) return fail(CLODE_ERR_STATE, "trajectory_stream: nPts == 0");
+    if (s->spec.staged) return fail(CLODE_ERR_INVALID, "trajectory_stream: not available with staged_trajectory programs");
+    if (chunk_rows == 0) return fail(CLODE_ERR_INVALID, "trajectory_stream: chunk_rows must be positive");
+    clode_sim::Scope scope(s);
+    int rc;
+    if ((rc = s->wait("trajectory_stream"))) return rc;
+    const size_t n = s->n, rs = s->real_size, nv = s->spec.n_var, na = s->spec.n_aux, nw = s->spec.n_wiener;
+    const size_t total_rows = (size_t)s->sp.max_store + 1; // the kernel can write row index max_store
+    const size_t R = std::min(chunk_rows, total_rows);
+    for (auto &c : s->chunk) {
+        if ((rc = s->alloc(c.t, rs * R * n, "chunk t"))) return rc;
+        if ((rc = s->alloc(c.x, rs * R * n * nv, "chunk x"))) return rc;
+        if ((rc = s->alloc(c.dx, rs * R * n * nv, "chunk dx"))) return rc;
+        if ((rc = s->alloc(c.aux, rs * std::max<size_t>(R * n * na, 1), "chunk aux"))) return rc;
+    }
+    if ((rc = s->alloc(s->rs_real, rs * (1 + nw) * n, "resume state"))) return rc;
+    if ((rc = s->alloc(s->rs_uint, 4 * 3 * n, "resume state"))) return rc;
+    if ((rc = s->alloc(s->chunk_flags, 8, "chunk flags"))) return rc;
+    if ((rc = s->alloc(s->n_stored, 4 * n, "nStored"))) return rc;
+    if (!s->flags_host && (rc = s->cu(s->d->cuMemHostAlloc((void **)&s->flags_host, 8, 0), "cuMemHostAlloc"))) return rc;
+
+    const HostOut out = {t, x, dx, aux};
+    std::future<int> copied[2];
+    auto drain = [&](int b) { return copied[b].valid() ? copied[b].get() : (int)CLODE_OK; };
+    float kernel_ms = 0.f;
+    rc = CLODE_OK;
+    for (size_t k = 0; k * R < total_rows; ++k) {
+        const int b = (int)(k & 1);
+        const size_t row_begin = k * R, row_end = std::min(row_begin + R, total_rows);
+        if ((rc = drain(b))) break; // the copy that last read this buffer set
+        clode_sim::Chunk &c = s->chunk[b];
+        // rows of instances that finished earlier read as zero
+        const Buffer *zero[] = {&c.t, &c.x, &c.dx, &c.aux, &s->chunk_flags};
+        for (const Buffer *z : zero)
+            if ((rc = s->cu(s->d->cuMemsetD8Async(z->ptr, 0, z->bytes, s->stream), "trajectory_stream: clear chunk"))) break;
+        if (rc) break;
+        KernelArgs a = s->args();
+        a.tr_t = c.t.ptr; a.tr_x = c.x.ptr; a.tr_dx = c.dx.ptr; a.tr_aux = c.aux.ptr;
+        a.rs_real = s->rs_real.ptr; a.rs_uint = s->rs_uint.ptr; a.chunk_flags = s->chunk_flags.ptr;
+        a.row_begin = (unsigned)row_begin; a.row_end = (unsigned)row_end; a.resume = k > 0;
+        if ((rc = s->launch_with(s->k_trajectory, a, "clode_trajectory (chunk)", true, true, false))) break;
+        if ((rc = s->cu(s->d->cuMemcpyDtoHAsync(s->flags_host, s->chunk_flags.ptr, 8, s->stream), "trajectory_stream: flags"))) break;
+        if ((rc = s->wait("clode_trajectory (chunk)"))) break;
+        kernel_ms += s->last_ms;
+        const bool any_live = s->flags_host[0] != 0;
+        // rows actually written by this launch, clipped to the max_store rows the API returns
+        const size_t stop = std::min<size_t>({(size_t)s->flags_host[1] + 1, row_end, (size_t)s->sp.max_store});
+        if (stop > row_begin)
+            copied[b] = std::async(std::launch::async, copy_chunk_out, s, b, row_begin, stop - row_begin, out);
+        if (!any_live) break;
+    }
+    const int rc0 = drain(0), rc1 = drain(1);
+    if (!rc) rc = rc0 ? rc0 : rc1;
+    s->last_ms = kernel_ms;
+    if (rc) return rc;
+    if (n_stored) return s->cu(s->d->cuMemcpyDtoH(n_stored, s->n_stored.ptr, 4 * n), "trajectory_stream: nStored");
+    return CLODE_OK;
+}
+
+// page-locked host memory for the streamed trajectory's output arrays (copies at full PCIe rate)
+void *clode_host_alloc(int device, size_t bytes)
+{
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (!d) { fail(CLODE_ERR_NO_DRIVER, why); return nullptr; }
+    CUdevice dev;
+    CUcontext ctx;
+    if (d->cuDeviceGet(&dev, device) != CUDA_SUCCESS || d->cuDevicePrimaryCtxRetain(&ctx, dev) != CUDA_SUCCESS) {
+        fail(CLODE_ERR_CUDA, "host_alloc: cannot retain the device context");
+        return nullptr;
+    }
+    d->cuCtxPushCurrent(ctx);
+    void *p = nullptr;
+    CUresult r = d->cuMemHostAlloc(&p, bytes, CU_MEMHOSTALLOC_PORTABLE);
+    CUcontext popped;
+    d->cuCtxPopCurrent(&popped);
+    d->cuDevicePrimaryCtxRelease(dev);
+    if (r != CUDA_SUCCESS) { fail(CLODE_ERR_MEMORY, "host_alloc: " + cu_error(d, r)); return nullptr; }
+    return p;
+}
+
+void clode_host_free(void *p)
+{
+    std::string why;
+    DriverApi *d = driver(&why);
+    if (d && p) d->cuMemFreeHost(p);
 }
 
 int clode_sim_enqueue(clode_sim *s, int kernel, int initialize)

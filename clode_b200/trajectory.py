@@ -58,7 +58,11 @@ class TrajectorySimulator(Simulator):
         platform_id: Optional[int] = None,
         device_id: Optional[int] = None,
         device_ids: Optional[List[int]] = None,
+        stream_chunk_rows: Optional[int] = None,
     ) -> None:
+        # not in the reference (TODO at clode/trajectory.py:166): integrate in launches of `stream_chunk_rows` stored
+        # points, copying each chunk to the host while the next one integrates; results are identical
+        self._stream_chunk_rows = int(stream_chunk_rows or 0)
         super().__init__(variables=variables, parameters=parameters, aux=aux, num_noise=num_noise, src_file=src_file,
                          rhs_equation=rhs_equation, supplementary_equations=supplementary_equations, stepper=stepper,
                          dt=dt, dtmax=dtmax, abstol=abstol, reltol=reltol, max_steps=max_steps, max_store=max_store,
@@ -69,6 +73,12 @@ class TrajectorySimulator(Simulator):
     def _create_integrator(self) -> None:
         self._integrator = TrajectorySimulatorBase(self._pi, self._stepper.value, self._single_precision, self._runtime,
                                                    _clode_root_dir)
+        self._integrator.set_stream_chunk(self._stream_chunk_rows)
+
+    def set_stream_chunk(self, rows: Optional[int]) -> None:
+        """0 / None: one launch holding all max_store points on the device (the reference's scheme); > 0: streamed"""
+        self._stream_chunk_rows = int(rows or 0)
+        self._integrator.set_stream_chunk(self._stream_chunk_rows)
 
     def trajectory(self, t_span=None, update_x0: bool = True, fetch_results: bool = True):
         if t_span is not None:

@@ -147,6 +147,20 @@ CLODE_API int clode_sim_observer_initialized(clode_sim *sim, int *flag);
 CLODE_API int clode_sim_trajectory(clode_sim *sim);           /* CLODEtrajectory::trajectory (:97-130)          */
 CLODE_API int clode_sim_shift_x0(clode_sim *sim);             /* CLODE::shiftX0 (CLODE.cpp:502-515), device to device */
 
+/* Streamed trajectory: the same integration and the same results as clode_sim_trajectory followed by
+ * clode_sim_get(CLODE_BUF_T / _X / _DX / _AUX) and clode_sim_get_n_stored, but cut into launches of `chunk_rows`
+ * stored points.  The device holds two chunks instead of all max_store rows, and the copy of chunk k to the host
+ * overlaps the integration of chunk k+1.  Replaces the single nPts*max_store allocation of
+ * CLODEtrajectory::resizeTrajectoryVariables (CLODEtrajectory.cpp:45-95; "TODO" at :47 and clode/trajectory.py:166)
+ * and the four copies of CLODEtrajectory::getT/getX/getDx/getAux (:132-205).
+ * Host arrays are full size and may be NULL to skip an output: t[max_store][n], x[max_store][nVar][n],
+ * dx[max_store][nVar][n], aux[max_store][nAux][n], n_stored[n]; rows at or beyond an instance's n_stored read 0.
+ * Arrays from clode_host_alloc are copied at the full PCIe rate; any other host memory works, slower. */
+CLODE_API int clode_sim_trajectory_stream(clode_sim *sim, size_t chunk_rows, double *t, double *x, double *dx,
+                                          double *aux, int *n_stored);
+CLODE_API void *clode_host_alloc(int device, size_t bytes); /* page-locked host memory; NULL on failure */
+CLODE_API void clode_host_free(void *p);
+
 /* Non-blocking variants, for callers that drive several GPUs from one thread (one clode_sim per
  * device, the reference's unused `OpenCLResource(platformID, std::vector<deviceIDs>)` hook,
  * OpenCLResource.hpp:104): enqueue on every shard, then wait on every shard.  `kernel` is one of

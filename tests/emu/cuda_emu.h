@@ -63,3 +63,4 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define __tanf emu__tanf
 #define __powf emu__powf
 #define __CUDACC_EMU__ 1
+static inline unsigned int atomicMax(unsigned int *p, unsigned int v) { unsigned int o = *p; if (v > o) *p = v; return o; }

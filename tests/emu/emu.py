@@ -37,7 +37,9 @@ class KernelArgs(ctypes.Structure):
         ("op_dx_down", ctypes.c_double), ("op_eps_dx", ctypes.c_double),
         ("n", ctypes.c_ulonglong),
     ] + [(k, ctypes.c_void_p) for k in ("x0", "pars", "xf", "rng", "dt", "tf", "steps", "od_real", "od_uint", "F",
-                                        "tr_t", "tr_x", "tr_dx", "tr_aux", "n_stored", "queue")]
+                                        "tr_t", "tr_x", "tr_dx", "tr_aux", "n_stored", "queue",
+                                        "rs_real", "rs_uint", "chunk_flags")] + [
+        ("row_begin", ctypes.c_uint), ("row_end", ctypes.c_uint), ("resume", ctypes.c_uint)]
 
 
 def _ptr(a):
@@ -94,6 +96,7 @@ class EmuLib:
                                                                  op.dx_up_threshold, op.dx_down_threshold)
             a.op_eps_dx = op.eps_dx
         a.n = n
+        a.row_begin, a.row_end, a.resume = 0, 0xFFFFFFFF, 0
         for k, v in bufs.items():
             setattr(a, k, _ptr(v) if v is not None else None)
         return a
@@ -145,3 +148,36 @@ class EmuLib:
         self.lib.emu_trajectory(ctypes.byref(a))
         return dict(t=t, x=x, dx=dx, aux=aux, n_stored=nst, xf=b["xf"], tf=b["tf"], dt=b["dt"], rng=b["rng"],
                     rows=rows, steps=b["steps"])
+
+    def trajectory_stream(self, tspan, x0, pars, sp, dt, rng, chunk_rows):
+        """the chunked trajectory exactly as clode_sim_trajectory_stream drives it (clode_rt.cpp): launches of
+        `chunk_rows` stored points into a chunk-sized buffer, state carried in xf/tf/dt/rng + rs_real/rs_uint"""
+        n = len(dt)
+        b = self._prep(x0, pars, dt, rng, n)
+        rows, total = sp.max_store, sp.max_store + 1
+        R = min(chunk_rows, total)
+        nv, na = self.n_var, self.n_aux
+        out = dict(t=np.zeros(rows * n, self.real), x=np.zeros(rows * n * nv, self.real),
+                   dx=np.zeros(rows * n * nv, self.real), aux=np.zeros(max(1, rows * n * na), self.real))
+        nst = np.zeros(n, np.int32)
+        rs_real = np.zeros((1 + self.n_wiener) * n, self.real)
+        rs_uint = np.zeros(3 * n, np.uint32)
+        launches = 0
+        for k in range((total + R - 1) // R):
+            row_begin, row_end = k * R, min(k * R + R, total)
+            c = dict(t=np.zeros(R * n, self.real), x=np.zeros(R * n * nv, self.real), dx=np.zeros(R * n * nv, self.real),
+                     aux=np.zeros(max(1, R * n * na), self.real))
+            flags = np.zeros(2, np.uint32)
+            a = self._args(tspan, sp, None, n, dict(b, tr_t=c["t"], tr_x=c["x"], tr_dx=c["dx"], tr_aux=c["aux"], n_stored=nst,
+                                                    rs_real=rs_real, rs_uint=rs_uint, chunk_flags=flags))
+            a.row_begin, a.row_end, a.resume = row_begin, row_end, int(k > 0)
+            self.lib.emu_trajectory(ctypes.byref(a))
+            launches += 1
+            stop = min(int(flags[1]) + 1, row_end, rows)
+            for key, width in (("t", 1), ("x", nv), ("dx", nv), ("aux", na)):
+                if stop > row_begin and width:
+                    out[key][row_begin * width * n:stop * width * n] = c[key][:(stop - row_begin) * width * n]
+            if not flags[0]:
+                break
+        return dict(out, n_stored=nst, xf=b["xf"], tf=b["tf"], dt=b["dt"], rng=b["rng"], rows=rows, steps=b["steps"],
+                    launches=launches)

@@ -71,3 +71,47 @@ def test_device_code_single_precision():
     A, B = EmuLib(cfg), restate.OracleLib(cfg)
     assert_bit_equal(run_oracle(A, "features", ts, x0, pars, sp, op), run_oracle(B, "features", ts, x0, pars, sp, op),
                      "single precision")
+
+
+def _streamed_equals_whole(whole, parts, n, widths, label):
+    """rows < n_stored (capped at the max_store rows the API returns) of every instance are bit-identical; rows
+    beyond read zero; final state, RNG words and counters are identical"""
+    rows = parts["rows"]
+    assert whole["rows"] == rows + 1
+    for key in ("n_stored", "xf", "tf", "dt", "rng", "steps"):
+        assert np.array_equal(np.asarray(whole[key]).view(np.uint8), np.asarray(parts[key]).view(np.uint8)), f"{label}: {key}"
+    kept = np.minimum(whole["n_stored"].astype(np.int64) + 1, rows)  # row index n_stored is the last one written
+    for key, width in widths.items():
+        if width == 0:
+            continue
+        a = whole[key][:rows * width * n].reshape(rows, width, n)
+        b = parts[key].reshape(rows, width, n)
+        live = np.arange(rows)[:, None, None] < kept[None, None, :]
+        live = np.broadcast_to(live, a.shape)
+        assert np.array_equal(a[live].view(np.uint64), b[live].view(np.uint64)), f"{label}: {key}"
+        assert not b[~live].any(), f"{label}: {key} rows beyond n_stored must read zero"
+
+
+@pytest.mark.parametrize("model,stepper,dt,nout,max_store,chunks", [
+    ("chay_keizer", "rk4", 0.5, 1, 120, (1, 7, 50, 121, 500)),       # fixed step, cut off by max_store
+    ("vanderpol", "heun", 0.05, 3, 400, (16, 64)),                    # nout > 1, runs to t_end
+    ("lorenz63", "dopri5", 0.01, 1, 300, (5, 33, 128)),               # adaptive: instances store at different rates
+    ("lactotroph", "bs23", 0.1, 2, 150, (10, 64)),
+    ("lactotroph_noise", "seuler", 0.05, 1, 90, (1, 8, 40)),          # RNG words, cached variate, pending noise
+])
+def test_streamed_trajectory_matches_single_launch(model, stepper, dt, nout, max_store, chunks):
+    """the chunked trajectory (clode_sim_trajectory_stream's launch sequence, replayed on the
+    emulated device code) produces the rows, counts and final state of the single-launch kernel bit for bit."""
+    n = 6
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[0] + (ts[1] - ts[0]) / 20)
+    sp = Solver(dt=dt, dtmax=1.0, abstol=1e-6, reltol=1e-5, max_steps=100000, max_store=max_store, nout=nout)
+    cfg = Config(model, stepper, math="pm")
+    lib = EmuLib(cfg)
+    whole = run_oracle(lib, "trajectory", ts, x0, pars, sp, None)
+    widths = dict(t=1, x=lib.n_var, dx=lib.n_var, aux=lib.n_aux)
+    for chunk_rows in chunks:
+        d, rng = np.full(n, sp.dt), __import__("oracle.common", fromlist=["seed_states"]).seed_states(1, n)
+        parts = lib.trajectory_stream(ts, x0, pars, sp, d, rng, chunk_rows)
+        _streamed_equals_whole(whole, parts, n, widths, f"{model}/{stepper} chunk_rows={chunk_rows}")
+        assert parts["launches"] <= -(-(max_store + 1) // min(chunk_rows, max_store + 1))

@@ -177,6 +177,37 @@ def test_trajectory_store_limit_and_shapes(clode):
     assert np.array_equal(np.asarray(sim._integrator.get_n_stored()), np.full(70, 40))
 
 
+def test_streamed_trajectory_through_the_front_end(clode):
+    """`stream_chunk_rows`: chunked launches with overlapped copy-out, on one runtime object and on
+    in-process shards (device_ids=[0, 0, 0]); the TrajectoryOutput objects are identical to the single-launch ones."""
+    kw = dict(src_file=model("chay_keizer"), variables={"v": -50.0, "n": 0.01, "c": 0.12},
+              parameters={"gca": 800.0, "gkca": 750.0, "kpmca": 0.12}, single_precision=False,
+              stepper=clode.Stepper.rk4, dt=0.5, t_span=(0.0, 300.0), max_store=400, nout=2, platform_id=0)
+    gca = np.linspace(550.0, 1050.0, 70)
+
+    def run(**extra):
+        sim = clode.TrajectorySimulator(**kw, **extra)
+        sim.set_ensemble(parameters={"gca": gca})
+        res = sim.trajectory()
+        return res, sim.get_final_state(), np.asarray(sim._integrator.get_n_stored())
+
+    base = run(device_ids=[0])
+    for extra in (dict(device_ids=[0], stream_chunk_rows=16), dict(device_ids=[0, 0, 0], stream_chunk_rows=64),
+                  dict(device_ids=[0], stream_chunk_rows=100000)):
+        other = run(**extra)
+        assert np.array_equal(base[2], other[2]) and np.array_equal(base[1], other[1])
+        for a, b in zip(base[0], other[0]):
+            assert np.array_equal(a.t, b.t) and np.array_equal(a.to_ndarray("x"), b.to_ndarray("x"))
+            assert np.array_equal(a.to_ndarray("dx"), b.to_ndarray("dx"))
+    # switching back to the single launch on the same object
+    sim = clode.TrajectorySimulator(**kw, device_ids=[0], stream_chunk_rows=8)
+    sim.set_ensemble(parameters={"gca": gca})
+    a = sim.trajectory(update_x0=False)
+    sim.set_stream_chunk(0)
+    b = sim.trajectory(update_x0=False)
+    assert all(np.array_equal(p.t, q.t) and np.array_equal(p.to_ndarray("x"), q.to_ndarray("x")) for p, q in zip(a, b))
+
+
 def test_in_process_two_gpus(clode, rt):
     """device_ids=[0, 1]: one runtime object per physical GPU, launches overlap, results identical to one GPU"""
     if rt.device_count() < 2:

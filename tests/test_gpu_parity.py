@@ -19,7 +19,7 @@ import pytest
 from golden_cases import CASES, case_inputs
 from oracle import ref, restate
 from oracle.common import Config, Observer, Solver, seed_states
-from problems import ensemble
+from problems import MODELS, ensemble
 from util import GpuRun, assert_bit_equal, run_oracle
 
 pytestmark = pytest.mark.gpu
@@ -336,6 +336,75 @@ def test_cuda_staged_trajectory_bit_exact(rt, model, stepper, n, nout, max_store
             m = np.broadcast_to(stored[:, None, :], (rows, width, n))
             assert np.array_equal(r[k].reshape(rows, width, n)[m], o[k].reshape(rows, width, n)[m]), k
     assert_bit_equal(r, o, "staged trajectory", keys=["n_stored", "xf", "tf", "dt", "rng"])
+    g.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# streamed trajectory: chunked launches, copy-out overlapped with the next chunk
+@pytest.mark.parametrize("model,stepper,n,nout,max_store,chunk_rows,pinned,bit_exact", [
+    ("chay_keizer", "rk4", 1000, 1, 50, 7, True, True),          # stops on max_store; last chunk partial
+    ("chay_keizer", "rk4", 1000, 1, 50, 1000, False, True),      # one chunk holds everything
+    ("lorenz63", "dopri5", 777, 1, 400, 64, True, True),         # adaptive: instances finish in different chunks
+    ("lorenz63", "dopri5", 777, 2, 400, 33, False, False),       # production arithmetic, pageable host arrays
+    ("lactotroph", "bs23", 300, 1, 120, 16, True, True),
+    ("lactotroph_noise", "seuler", 512, 4, 30, 4, True, True),   # RNG state, cached variate, pending noise
+    ("vanderpol", "heun", 131, 3, 90, 1, False, True),           # one row per launch
+])
+def test_cuda_streamed_trajectory_equals_single_launch(rt, model, stepper, n, nout, max_store, chunk_rows, pinned, bit_exact):
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[0] + (ts[1] - ts[0]) / 10)
+    sp = Solver(dt=0.05, dtmax=1.0, abstol=1e-6, reltol=1e-5, max_steps=100000, max_store=max_store, nout=nout)
+    g = GpuRun(rt, model, stepper, bit_exact=bit_exact)
+    g.setup(ts, x0, pars, sp, None, seed=4)
+    whole = g.trajectory()
+    launches = g.sim.launch_count()
+    g.setup(ts, x0, pars, sp, None, seed=4)
+    g.sim.set_dt(np.full(n, sp.dt))
+    parts = dict(g.sim.trajectory_stream(chunk_rows, pinned=pinned))
+    parts.update(g.common())
+    assert g.sim.launch_count() - launches <= -(-(max_store + 1) // min(chunk_rows, max_store + 1))
+    if bit_exact:  # and against the oracle
+        o = run_oracle(restate.OracleLib(Config(model, stepper, math="pm")), "trajectory", ts, x0, pars, sp, None, seed=4)
+        assert_bit_equal(whole, o, "single launch", keys=["n_stored", "xf", "tf", "dt", "rng"])
+    nv, na = MODELS[model][0], MODELS[model][2]
+    rows = max_store
+    # the FSAL slope is recomputed at a chunk boundary; with FMA contraction (production build) the two inlined
+    # copies of the user's RHS may round differently, so only the bit-exact tier is compared bit for bit
+    same = (lambda a, b: np.array_equal(a, b)) if bit_exact else (lambda a, b: np.allclose(a, b, rtol=1e-6, atol=1e-9))
+    assert np.array_equal(whole["n_stored"], parts["n_stored"]) or not bit_exact
+    kept = np.minimum(parts["n_stored"].astype(np.int64) + 1, rows)
+    for k, width in (("t", 1), ("x", nv), ("dx", nv), ("aux", na)):
+        if not width:
+            continue
+        a = whole[k][:rows * width * n].reshape(rows, width, n)
+        b = np.asarray(parts[k]).reshape(rows, width, n)
+        live = np.broadcast_to(np.arange(rows)[:, None, None] < kept[None, None, :], a.shape)
+        if bit_exact:
+            assert np.array_equal(a[live], b[live]), k
+        else:  # chaotic instances decorrelate: compare the early part of every trajectory
+            early = live & (np.arange(rows)[:, None, None] < 40)
+            assert np.allclose(a[early], b[early], rtol=1e-5, atol=1e-7), k
+        assert not b[~live].any(), f"{k}: rows beyond n_stored must read zero"
+    for k in ("xf", "tf", "dt", "rng", "steps"):
+        if bit_exact:
+            assert np.array_equal(whole[k], parts[k]), k
+    g.close()
+
+
+def test_cuda_streamed_trajectory_single_precision_and_skipped_outputs(rt):
+    n, max_store = 200, 60
+    ts, x0, pars = ensemble("chay_keizer", n)
+    sp = Solver(dt=0.5, dtmax=1.0, max_steps=100000, max_store=max_store, nout=1)
+    g = GpuRun(rt, "chay_keizer", "rk4", bit_exact=False, single=True)
+    g.setup((0.0, 100.0), x0, pars, sp, None, seed=1)
+    whole = g.trajectory()
+    g.setup((0.0, 100.0), x0, pars, sp, None, seed=1)
+    g.sim.set_dt(np.full(n, sp.dt))
+    parts = g.sim.trajectory_stream(9, want=("t", "x"))
+    assert parts["dx"] is None
+    assert np.array_equal(parts["n_stored"], whole["n_stored"])
+    rows = max_store
+    assert np.array_equal(whole["t"][:rows * n], parts["t"]) and np.array_equal(whole["x"][:rows * n * 3], parts["x"])
     g.close()
 
 
