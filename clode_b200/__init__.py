@@ -12,11 +12,17 @@ _FRONT_END = ["CLDeviceType", "CLVendor", "DeviceInfo", "PlatformInfo", "OpenCLR
               "print_opencl", "query_opencl", "LogLevel", "get_log_level", "set_log_level", "set_log_pattern",
               "ProblemInfo", "SolverParams", "Stepper", "Simulator", "FeatureSimulator", "Observer", "ObserverParams",
               "ObserverOutput", "TrajectorySimulator", "TrajectoryOutput"]
-__all__ = list(_FRONT_END)
+_TEXT_FRONT_ENDS = {"OpenCLConverter": "function_converter", "OpenCLRhsEquation": "function_converter",
+                    "convert_str_to_opencl": "function_converter", "convert_xpp_file": "xpp_parser",
+                    "read_ode_parameters": "xpp_parser", "format_opencl_rhs": "xpp_parser"}
+__all__ = list(_FRONT_END) + list(_TEXT_FRONT_ENDS)
 
 
 def __getattr__(name):
     # lazy: `import clode_b200` must work before the extension is built (build.py lives in this package)
+    if name in _TEXT_FRONT_ENDS:  # pure Python: Python / XPP -> OpenCL-C source (clode/__init__.py exports the same names)
+        import importlib
+        return getattr(importlib.import_module("." + _TEXT_FRONT_ENDS[name], __name__), name)
     if name in _FRONT_END:
         from . import features, runtime, solver, trajectory
         from .cpp import clode_cpp_wrapper as w

@@ -3,9 +3,9 @@
 Mirror of the reference's clode/solver.py:49-748 (`Stepper`, `Simulator`): same constructor
 arguments, method names, array conventions (ensemble arrays are (ensemble_size, n) matrices, handed
 to the C++ layer flattened in Fortran order, clode/solver.py:478-481) and ensemble-building rules.
-The right-hand side comes from an OpenCL-C source file (`src_file`); the Python->OpenCL and
-XPP->OpenCL transpilers of the reference are text generators outside this package's scope
- — their OUTPUT files are accepted here unchanged.
+The right-hand side comes from an OpenCL-C source file (`src_file`), an XPP file (`src_file="m.xpp"`,
+converted by `xpp_parser`) or a typed Python function (`rhs_equation=`, with `supplementary_equations=` as
+helpers, converted by `function_converter`) — clode/solver.py:220-252.
 """
 from __future__ import annotations
 
@@ -69,10 +69,7 @@ class Simulator:
             raise ValueError("Cannot specify both src_file and rhs_equation")
         if src_file is None and rhs_equation is None:
             raise ValueError("Must specify either src_file or rhs_equation")
-        if rhs_equation is not None or (src_file or "").endswith(".xpp"):
-            raise NotImplementedError(
-                "Python / XPP right-hand sides are converted to OpenCL C by the reference's clode.function_converter / "
-                "clode.xpp_parser; pass the generated .cl file as src_file")
+        src_file = self._handle_clode_rhs_cl_file(src_file, rhs_equation, supplementary_equations)
         self._pi = ProblemInfo(src_file, list(variables.keys()), list(parameters.keys()), list(aux or []), num_noise)
         self._stepper = stepper
         self._single_precision = single_precision
@@ -95,6 +92,29 @@ class Simulator:
         self._ensemble_shape: Tuple = (1,)
         self._set_problem_data(np.array(list(variables.values()), dtype=np.float64, ndmin=2),
                                np.array(list(parameters.values()), dtype=np.float64, ndmin=2))
+
+    @staticmethod
+    def _handle_clode_rhs_cl_file(src_file, rhs_equation, supplementary_equations) -> str:
+        """clode/solver.py:220-252: `.xpp` files and Python functions become an OpenCL-C file.  The reference writes
+        `clode_rhs.cl` into the working directory; here the generated text goes to a private temporary file, so
+        concurrent simulators (and read-only working directories) do not collide."""
+        if src_file is not None:
+            if src_file.endswith(".xpp"):
+                from .xpp_parser import convert_xpp_file
+                return convert_xpp_file(src_file)
+            return src_file
+        import os
+        import tempfile
+
+        from .function_converter import OpenCLConverter
+        converter = OpenCLConverter()
+        for eq in supplementary_equations or []:
+            converter.convert_to_opencl(eq)
+        text = converter.convert_to_opencl(rhs_equation, mutable_args=[3, 4], function_name="getRHS")
+        fd, path = tempfile.mkstemp(prefix="clode_rhs_", suffix=".cl")
+        with os.fdopen(fd, "w") as f:
+            f.write(text)
+        return path
 
     # ---- properties (clode/solver.py:83-119) ---------------------------------------------------
     @property

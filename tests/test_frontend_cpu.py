@@ -58,11 +58,18 @@ def test_log_level_round_trip():
     clode.set_log_level(previous)
 
 
-def test_python_and_xpp_sources_are_rejected_with_a_pointer():
-    with pytest.raises(NotImplementedError):
-        clode.Simulator(variables={"x": 0.0}, parameters={"a": 1.0}, rhs_equation=lambda *a: None)
-    with pytest.raises(ValueError):
+def test_source_arguments_are_validated_like_the_reference():
+    """clode/solver.py:228-250"""
+    with pytest.raises(ValueError, match="Cannot specify both"):
+        clode.Simulator(variables={"x": 0.0}, parameters={"a": 1.0}, src_file="a.cl", rhs_equation=lambda *a: None)
+    with pytest.raises(ValueError, match="Must specify either"):
         clode.Simulator(variables={"x": 0.0}, parameters={"a": 1.0})
+
+    def untyped(t, x, p, dx, aux, w):  # the converter refuses it before any device work starts
+        dx[0] = -x[0]
+
+    with pytest.raises(TypeError, match="must have a return type"):
+        clode.Simulator(variables={"x": 0.0}, parameters={"a": 1.0}, rhs_equation=untyped)
 
 
 def test_missing_gpu_is_a_loud_error_not_a_fallback(rt):

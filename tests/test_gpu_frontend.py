@@ -177,6 +177,34 @@ def test_trajectory_store_limit_and_shapes(clode):
     assert np.array_equal(np.asarray(sim._integrator.get_n_stored()), np.full(70, 40))
 
 
+def test_python_and_xpp_right_hand_sides(clode, tmp_path):
+    """test/test_vdp.py:33-95 passes the Van der Pol system as a Python function (`rhs_equation=`), and
+    test/test_xpp_parser.py:21 as an XPP file; both must give exactly what the hand-written .cl gives"""
+    src = ("def vdp(t: float, var: List[float], par: List[float], derivatives: List[float], aux: List[float], "
+           "wiener: List[float]) -> None:\n    mu: float = par[0]\n    x: float = var[0]\n    y: float = var[1]\n"
+           "    dx: float = y\n    dy: float = mu * (1 - x * x) * y - x\n    derivatives[0] = dx\n    derivatives[1] = dy\n")
+    mod = tmp_path / "vdp_module.py"
+    mod.write_text("from typing import List\n\n\n" + src)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vdp_module", mod)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    xpp = tmp_path / "vdp.xpp"
+    xpp.write_text("init x=1.0\ninit y=1.0\npar mu=1.0\ny' = mu * (1 - x*x) * y - x\nx' = y\n")
+    kw = dict(variables={"x": 1.0, "y": 1.0}, parameters={"mu": 1.0}, observer=clode.Observer.threshold_2,
+              stepper=clode.Stepper.dormand_prince, t_span=(0.0, 200.0), single_precision=False)
+    mus = [0.01, 0.5, 1.0, 2.0, 4.0]
+    results = []
+    for source in (dict(src_file=model("vanderpol")), dict(rhs_equation=m.vdp), dict(src_file=str(xpp))):
+        integ = clode.FeatureSimulator(**source, **kw)
+        integ.set_ensemble(parameters={"mu": mus})
+        integ.features()
+        results.append((integ.get_observer_results().to_ndarray(), integ.get_final_state()))
+    for other in results[1:]:
+        assert np.allclose(results[0][0], other[0], rtol=1e-9, atol=1e-12, equal_nan=True)
+        assert np.allclose(results[0][1], other[1], rtol=1e-9, atol=1e-12)
+
+
 def test_streamed_trajectory_through_the_front_end(clode):
     """`stream_chunk_rows`: chunked launches with overlapped copy-out, on one runtime object and on
     in-process shards (device_ids=[0, 0, 0]); the TrajectoryOutput objects are identical to the single-launch ones."""
