@@ -45,7 +45,17 @@ struct ObserverParams {
 // step for `basic`).  open_means() converts the stored means on entry, S_0 = m_0 * (t_prev - t_start) — this also
 // reproduces what the recurrence does when a continued run restarts the clock — and close_means() divides
 // once before the features are emitted / the state is stored, so the persistent layout holds means in both tiers.
-#if CLODE_EXACT_ARITH
+#if CLODE_FAST_SINGLE
+// single precision keeps the recurrence (an FP32 running sum over 1e4..1e6 steps would lose digits) but forms the
+// weight dt / span once per step and updates every mean with one FMA
+#define CLODE_INTEGRAL_MEANS 0
+struct MeanWeight {
+    realtype w;
+};
+CLODE_DEV MeanWeight mean_weight(realtype dt, realtype span) { MeanWeight w = {div_nr(dt, span)}; return w; }
+CLODE_DEV realtype mean_time(realtype mean, realtype v, const MeanWeight &w) { return fmaf(v - mean, w.w, mean); }
+CLODE_DEV realtype mean_step(realtype mean, realtype v, realtype dt, realtype span) { return fmaf(v - mean, div_nr(dt, span), mean); }
+#elif CLODE_EXACT_ARITH
 #define CLODE_INTEGRAL_MEANS 0
 struct MeanWeight {
     realtype dt, span;

@@ -46,6 +46,13 @@ struct SolverParams {
 #else
 #define CLODE_EXACT_ARITH 0
 #endif
+// Production single precision (the reference's Python default): FP32 has native min/max/abs, so only the
+// engine's own divisions, the controller root and the step floor get cheaper sequences (all within a few ulp).
+#if defined(CLODE_SINGLE_PRECISION) && !defined(CLODE_REFERENCE_MATH) && !defined(__CUDACC_EMU__)
+#define CLODE_FAST_SINGLE 1
+#else
+#define CLODE_FAST_SINGLE 0
+#endif
 
 // fmax/fmin where the SECOND operand is known not to be NaN (a running extreme that started finite, a
 // solver parameter, ...).  Same value as fmax(v, m) / fmin(v, m) for every input — a NaN v yields m —
@@ -80,7 +87,17 @@ CLODE_DEV double opaque(const double c) { double r; asm("mov.f64 %0, %1;" : "=d"
 // slow path (the divisors here are max(|x|, abstol/reltol) and elapsed times: normal, finite numbers).
 // libdevice's correctly-rounded division costs 8 FP64 + ~6 control instructions per call and a Lorenz
 // dopri5 attempt makes four of them.  The user's RHS keeps the IEEE `/`.
-#if CLODE_EXACT_ARITH
+#if CLODE_FAST_SINGLE
+// MUFU.RCP + one Newton step + multiply: <= 1.5 ulp, branch-free (the IEEE float division is ~10 instructions
+// with a range check and a slow-path call)
+CLODE_DEV float div_nr(const float a, const float b)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    r = fmaf(r, fmaf(-b, r, 1.0f), r);
+    return a * r;
+}
+#elif CLODE_EXACT_ARITH
 CLODE_DEV realtype div_nr(const realtype a, const realtype b) { return a / b; }
 #else
 CLODE_DEV double div_nr(const double a, const double b)
@@ -280,7 +297,15 @@ struct Controller {
     realtype scale; // 0.8 * reltol^(1/(p+1))   (production double only)
     int floor_hi_min; // step_floor's exponent-field form applies to hi(t) in [floor_hi_min, 0x7ff00000): empty unless t_end > 0
 };
-#if defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH)
+#if CLODE_FAST_SINGLE
+#define CLODE_EXACT_CONTROLLER 0
+// single precision: the SFU pair lg2/ex2 alone is within ~8 ulp of pow (OpenCL C allows 16)
+CLODE_DEV float controller_factor(const Controller &c, float nerr)
+{
+    const float x = fminf(fmaxf(nerr, 1e-30f), 1e30f);
+    return c.scale * exp2f((-1.0f / (ERR_ORDER + 1.0f)) * __log2f(x));
+}
+#elif defined(CLODE_BITEXACT) || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_REFERENCE_MATH)
 #define CLODE_EXACT_CONTROLLER 1
 CLODE_DEV realtype controller_factor(const Controller &c, realtype nerr)
 {
@@ -316,7 +341,11 @@ CLODE_DEV Controller make_controller(const SolverParams &sp, const realtype t_en
     c.reltol = sp.reltol;
     c.floor_ = sp.abstol / sp.reltol;
     c.scale = RCONST(0.8) * pow(sp.reltol, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
+#if defined(CLODE_SINGLE_PRECISION)
+    c.floor_hi_min = t_end > ZERO ? (20 << 23) : 0x7f800000;
+#else
     c.floor_hi_min = t_end > ZERO ? (49 << 20) : 0x7ff00000;
+#endif
     return c;
 }
 
@@ -326,6 +355,13 @@ CLODE_DEV Controller make_controller(const SolverParams &sp, const realtype t_en
 CLODE_DEV realtype step_floor(const realtype t, const realtype t_end, const int fast_hi_min)
 {
 #if defined(CLODE_SINGLE_PRECISION)
+#if CLODE_FAST_SINGLE
+    {   // 0 < t <= t_end, biased exponent E >= 20: 16 ulp(t) = 2^(E-146), from the exponent field (as for double below)
+        const int bits = __float_as_int(t);
+        if (bits >= fast_hi_min && bits < 0x7f800000)
+            return __int_as_float((bits & 0x7f800000) - (19 << 23));
+    }
+#endif
     return RCONST(16.0) * fabs(fabs(nextafter(t, RCONST(1.1) * t_end)) - t);
 #else
 #if !CLODE_EXACT_ARITH

@@ -733,7 +733,13 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
         candidates.push_back(spec.min_blocks);
         spill_limit.push_back(1 << 30);
     } else {
+        // single precision: half the register footprint, so one extra candidate at 1024 threads/SM (<= 64 registers;
+        // C2 in FP32: 32.3 ms against 33.7 ms at 640 threads/SM)
         const int most = std::max(1, 640 / spec.block);
+        if (spec.single && 1024 / spec.block > most) {
+            candidates.push_back(1024 / spec.block);
+            spill_limit.push_back(16);
+        }
         for (int m = most; m >= 1; --m) {
             candidates.push_back(m);
             const int warps = m * spec.block / 32;

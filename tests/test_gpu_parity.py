@@ -211,6 +211,39 @@ def test_cuda_single_precision(rt):
     g.close()
 
 
+@pytest.mark.parametrize("model,stepper,observer", [("lorenz63", "dopri5", "basic"), ("vanderpol", "bs23", "basicall"),
+                                                    ("lactotroph", "dopri5", "basicall")])
+def test_cuda_single_precision_adaptive(rt, model, stepper, observer):
+    """single precision, adaptive steppers: the production build forms the controller root with the SFU (lg2/ex2), the
+    engine's divisions with a Newton reciprocal and the step floor from the exponent field.  Against the oracle in
+    single precision (libm powf, IEEE division): accepted-step counts within 1 %, features within 5e-3 of the
+    feature's range over the ensemble (measured: <= 2e-3; non-chaotic instances; FP32 round-off already moves
+    individual steps, and extrema of slopes are taken at discrete step times)."""
+    n = 96
+    ts, x0, pars = ensemble(model, n)
+    if model == "lorenz63":  # r in [0.5, 20]: fixed points, no chaos
+        pars = np.concatenate([np.linspace(0.5, 20.0, n), np.full(n, 10.0), np.full(n, 8.0 / 3.0)])
+    ts = (0.0, 20.0 if model != "lactotroph" else 400.0)
+    sp = Solver(dt=0.01, dtmax=1.0, abstol=1e-5, reltol=1e-4, max_steps=1000000)
+    g = GpuRun(rt, model, stepper, observer, bit_exact=False, single=True)
+    g.setup(ts, x0, pars, sp, Observer())
+    r = g.features()
+    o = run_oracle(restate.OracleLib(Config(model, stepper, observer, single=True)), "features", ts, x0, pars, sp, Observer())
+    nf = len(r["F"]) // n
+    Fg, Fo = r["F"].reshape(nf, n), o["F"].astype(np.float64).reshape(nf, n)
+    so, sg = Fo[-1], r["steps"].astype(np.float64)  # the last feature of these observers is the step count
+    assert np.array_equal(Fg[-1], sg)
+    assert np.all(np.abs(so - sg) <= np.maximum(3.0, 0.01 * so)), (so[:8], sg[:8])
+    scale = np.maximum(np.abs(Fo).max(axis=1, keepdims=True), 1e-3)
+    keep = np.ones(nf, bool)
+    keep[-1] = False  # the step-count feature is compared above
+    worst = (np.abs(Fg - Fo) / scale)[keep].max(axis=1)
+    print("single precision, worst feature deviation / range:", worst)
+    assert np.all(worst <= 5e-3), worst
+    assert np.allclose(r["tf"], o["tf"].astype(np.float64), rtol=1e-5)
+    g.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # edge cases
 def test_cuda_edge_sizes_and_limits(rt):
