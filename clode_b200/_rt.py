@@ -35,7 +35,8 @@ class ProgramDesc(ctypes.Structure):
         ("e_var_ix", ctypes.c_int), ("n_store_events", ctypes.c_int), ("kernels", ctypes.c_int),
         ("bit_exact", ctypes.c_int), ("work_queue", ctypes.c_int), ("block_size", ctypes.c_int),
         ("min_blocks_per_sm", ctypes.c_int), ("staged_trajectory", ctypes.c_int),
-        ("observer_in_shared", ctypes.c_int),
+        ("observer_in_shared", ctypes.c_int), ("ieee_constant_division", ctypes.c_int),
+        ("library_exp", ctypes.c_int),
     ]
 
 
@@ -128,13 +129,16 @@ class Program:
     min_blocks_per_sm: int = 0
     staged_trajectory: bool = False
     observer_in_shared: bool = False
+    ieee_constant_division: bool = False
+    library_exp: bool = False
 
     def c(self) -> ProgramDesc:
         return ProgramDesc(self.rhs_source.encode(), self.stepper.encode(), self.observer.encode(),
                            int(self.single_precision), self.n_var, self.n_par, self.n_aux, self.n_wiener,
                            self.f_var_ix, self.e_var_ix, self.n_store_events, self.kernels,
                            int(self.bit_exact), int(self.work_queue), self.block_size, self.min_blocks_per_sm,
-                           int(self.staged_trajectory), int(self.observer_in_shared))
+                           int(self.staged_trajectory), int(self.observer_in_shared),
+                           int(self.ieee_constant_division), int(self.library_exp))
 
 
 class _PinnedBlock:

@@ -327,4 +327,11 @@ CLODE_DEV void quadraticInterpVertex(realtype t[], realtype y[], realtype *tv, r
 #define sin(x) pm_sin(x)
 #endif
 
+// ---- production double: exp() by table + short polynomial (fast_exp.cuh), unless the program asks for the library's
+#if defined(CLODE_DOUBLE_PRECISION) && !defined(CLODE_BITEXACT) && !defined(CLODE_REFERENCE_MATH) && \
+    !defined(CLODE_LIBRARY_EXP) && !defined(__CUDACC_EMU__)
+#include "fast_exp.cuh"
+#define exp(x) clode_fast_exp(x)
+#endif
+
 #endif // CLODE_CL_COMPAT_CUH

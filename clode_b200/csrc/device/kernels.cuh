@@ -24,6 +24,21 @@
 #ifndef CLODE_MIN_BLOCKS
 #define CLODE_MIN_BLOCKS 4
 #endif
+// Occupancy target (second __launch_bounds__ argument) per kernel: the kernels of one program carry very different
+// amounts of state — initializeObserver's warm-up pass holds four extents where the features pass holds the whole
+// thresh2 / nhood2 record — so the runtime picks each kernel's register budget separately (clode_sim_build).
+#ifndef CLODE_MIN_BLOCKS_TRANSIENT
+#define CLODE_MIN_BLOCKS_TRANSIENT CLODE_MIN_BLOCKS
+#endif
+#ifndef CLODE_MIN_BLOCKS_INIT
+#define CLODE_MIN_BLOCKS_INIT CLODE_MIN_BLOCKS
+#endif
+#ifndef CLODE_MIN_BLOCKS_FEATURES
+#define CLODE_MIN_BLOCKS_FEATURES CLODE_MIN_BLOCKS
+#endif
+#ifndef CLODE_MIN_BLOCKS_TRAJECTORY
+#define CLODE_MIN_BLOCKS_TRAJECTORY CLODE_MIN_BLOCKS
+#endif
 
 // Launch arguments: one struct in __constant__ memory (`clode_args`), written by the host
 // with an in-stream copy before each launch; every field is a warp-uniform constant-bank load.
@@ -222,7 +237,7 @@ struct TransientJob {
     __device__ __forceinline__ void end(size_t i) { store_instance(I, a, i, step); }
 };
 
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRANSIENT)
 clode_transient()
 {
     TransientJob job(clode_args);
@@ -312,7 +327,7 @@ struct WarmupJob {
     }
 };
 
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_INIT)
 clode_initialize_observer()
 {
     WarmupJob job(clode_args);
@@ -377,7 +392,7 @@ struct FeaturesJob {
     }
 };
 
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_FEATURES)
 clode_features()
 {
     FeaturesJob job(clode_args);
@@ -559,7 +574,7 @@ CLODE_DEV void tile_flush(realtype (*tile)[CLODE_BLOCK], const KernelArgs &a, co
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRAJECTORY)
 clode_trajectory()
 {
     const KernelArgs &a = clode_args;
@@ -613,7 +628,7 @@ clode_trajectory()
     if (valid) job.end(i);
 }
 #else
-extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS)
+extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRAJECTORY)
 clode_trajectory()
 {
     TrajectoryJob job(clode_args);

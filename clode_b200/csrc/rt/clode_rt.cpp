@@ -8,6 +8,7 @@
 #include "clode_rt.h"
 
 #include "cuda_dl.hpp"
+#include "ptx_pass.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -17,6 +18,7 @@
 #include <fstream>
 #include <sstream>
 #include <future>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -78,7 +80,10 @@ struct ProgramSpec {
     int f_var = 0, e_var = 0, n_store = 0;
     int kernels = CLODE_KERNEL_TRANSIENT;
     bool bit_exact = false, work_queue = false, staged = false, obs_smem = false;
+    bool library_exp = false; // keep CUDA's exp in production double builds (default: device/fast_exp.cuh)
+    bool const_div = true; // ptx_pass.hpp: divisions by literal constants without the Newton refinement of the literal
     int block = 128, min_blocks = 4;
+    int kernel_min_blocks[4] = {0, 0, 0, 0}; // transient, initializeObserver, features, trajectory; 0 = min_blocks
 };
 
 int parse_desc(const clode_program_desc *d, ProgramSpec &s)
@@ -101,6 +106,8 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.bit_exact = d->bit_exact != 0;
     if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
     s.work_queue = d->work_queue != 0;
+    s.const_div = !s.bit_exact && d->ieee_constant_division == 0;
+    s.library_exp = d->library_exp != 0;
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     s.block = d->block_size > 0 ? d->block_size : 128;
@@ -112,7 +119,8 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
 std::vector<std::string> compile_options(const ProgramSpec &s)
 {
     std::vector<std::string> o;
-    o.push_back("--gpu-architecture=sm_100a");
+    // with the PTX pass NVRTC stops at PTX (a virtual architecture) and nvJitLink runs ptxas on the rewritten text
+    o.push_back(s.const_div ? "--gpu-architecture=compute_100a" : "--gpu-architecture=sm_100a");
     o.push_back("--std=c++17");
     o.push_back("-default-device");
     o.push_back("-lineinfo");
@@ -129,9 +137,15 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     o.push_back("-DE_VAR_IX=" + std::to_string(s.e_var));
     o.push_back("-DCLODE_BLOCK=" + std::to_string(s.block));
     o.push_back("-DCLODE_MIN_BLOCKS=" + std::to_string(s.min_blocks));
+    static const char *kKernelBounds[4] = {"-DCLODE_MIN_BLOCKS_TRANSIENT=", "-DCLODE_MIN_BLOCKS_INIT=",
+                                           "-DCLODE_MIN_BLOCKS_FEATURES=", "-DCLODE_MIN_BLOCKS_TRAJECTORY="};
+    for (int k = 0; k < 4; ++k)
+        if (s.kernel_min_blocks[k] > 0 && s.kernel_min_blocks[k] != s.min_blocks)
+            o.push_back(kKernelBounds[k] + std::to_string(s.kernel_min_blocks[k]));
     if (s.kernels & CLODE_KERNEL_FEATURES) o.push_back("-DCLODE_WITH_FEATURES");
     if (s.kernels & CLODE_KERNEL_TRAJECTORY) o.push_back("-DCLODE_WITH_TRAJECTORY");
     if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
+    if (s.library_exp) o.push_back("-DCLODE_LIBRARY_EXP");
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
@@ -186,10 +200,98 @@ std::string cache_dir()
     return "/tmp/clode_cubin_cache";
 }
 
+std::string own_dir()
+{
+    Dl_info info;
+    if (dladdr((void *)&fnv1a, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        if (k != std::string::npos) return p.substr(0, k);
+    }
+    return ".";
+}
+
+// libclode_ptxas.so (csrc/rt/ptxas_shim.cpp): ptxas as a library, next to this library
+struct PtxasShim {
+    int (*assemble)(const char *, size_t, int, void **, size_t *, char **) = nullptr;
+    void (*release)(void *) = nullptr;
+    bool load()
+    {
+        const std::string path = own_dir() + "/libclode_ptxas.so";
+        void *h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) return false;
+        assemble = reinterpret_cast<decltype(assemble)>(dlsym(h, "clode_ptxas"));
+        release = reinterpret_cast<decltype(release)>(dlsym(h, "clode_ptxas_free"));
+        return assemble && release;
+    }
+};
+
+PtxasShim *ptxas_shim()
+{
+    static PtxasShim shim;
+    static bool ok = false;
+    static std::once_flag once;
+    std::call_once(once, [] { ok = shim.load(); });
+    return ok ? &shim : nullptr;
+}
+
+// PTX -> sm_100a cubin, no GPU needed.  Preferred: libclode_ptxas.so (whole-program ptxas, the same code generator
+// NVRTC embeds).  Fallback when that library was not built: nvJitLink, which assembles relocatable code — correct,
+// but __constant__ operands are re-loaded inside the time loop (see ptxas_shim.cpp) — and says so in the log.
+int assemble_ptx(const std::string &ptx, std::vector<char> &cubin, std::string &log)
+{
+    if (PtxasShim *shim = ptxas_shim()) {
+        void *out = nullptr;
+        size_t size = 0;
+        char *err = nullptr;
+        const int r = shim->assemble(ptx.data(), ptx.size(), 1, &out, &size, &err);
+        if (r != 0) {
+            std::string msg = "ptxas failed (" + std::to_string(r) + ")\n" + (err ? err : "") + "\n" + log;
+            if (err) shim->release(err);
+            return fail(CLODE_ERR_BUILD, msg);
+        }
+        cubin.assign((const char *)out, (const char *)out + size);
+        shim->release(out);
+        return CLODE_OK;
+    }
+    std::string why;
+    JitLinkApi *jl = jitlink(&why);
+    if (!jl) return fail(CLODE_ERR_NO_DRIVER, "libclode_ptxas.so is missing (python -m clode_b200.build) and " + why);
+    JitLinkApi::Handle h = nullptr;
+    const char *opts[] = {"-arch=sm_100a", "-lineinfo"};
+    int r = jl->Create(&h, 2, opts);
+    if (r != 0) return fail(CLODE_ERR_BUILD, "nvJitLinkCreate failed (" + std::to_string(r) + ")");
+    r = jl->AddData(h, JitLinkApi::INPUT_PTX, ptx.data(), ptx.size(), "clode_program.ptx");
+    if (r == 0) r = jl->Complete(h);
+    if (r != 0) {
+        size_t n = 0;
+        std::string err;
+        if (jl->GetErrorLogSize(h, &n) == 0 && n > 0) {
+            err.assign(n, '\0');
+            jl->GetErrorLog(h, &err[0]);
+        }
+        jl->Destroy(&h);
+        return fail(CLODE_ERR_BUILD, "ptxas (nvJitLink) failed (" + std::to_string(r) + ")\n" + err + "\n" + log);
+    }
+    size_t size = 0;
+    r = jl->GetLinkedCubinSize(h, &size);
+    if (r != 0 || size == 0) {
+        jl->Destroy(&h);
+        return fail(CLODE_ERR_BUILD, "nvJitLinkGetLinkedCubinSize failed");
+    }
+    cubin.resize(size);
+    r = jl->GetLinkedCubin(h, cubin.data());
+    jl->Destroy(&h);
+    if (r != 0) return fail(CLODE_ERR_BUILD, "nvJitLinkGetLinkedCubin failed");
+    log += "\n(libclode_ptxas.so not found: assembled with nvJitLink as relocatable code)";
+    return CLODE_OK;
+}
+
 int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &log)
 {
     // cache lookup
     std::string key_src = full_source(s);
+    if (s.const_div) key_src += ptxas_shim() ? "// ptx pass v1, assembled by libclode_ptxas\n" : "// ptx pass v1, assembled by nvJitLink\n";
     uint64_t h1 = fnv1a(key_src, 1469598103934665603ull), h2 = fnv1a(key_src, 0x9e3779b97f4a7c15ull);
     char name[64];
     std::snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
@@ -235,14 +337,31 @@ int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &lo
         return fail(CLODE_ERR_BUILD, std::string("NVRTC compilation failed (") + rtc->nvrtcGetErrorString(r) + ")\n" + log);
     }
     size_t size = 0;
-    r = rtc->nvrtcGetCUBINSize(prog, &size);
-    if (r != NVRTC_SUCCESS || size == 0) {
+    if (s.const_div) {
+        r = rtc->nvrtcGetPTXSize(prog, &size);
+        if (r != NVRTC_SUCCESS || size == 0) {
+            rtc->nvrtcDestroyProgram(&prog);
+            return fail(CLODE_ERR_BUILD, "nvrtcGetPTXSize failed");
+        }
+        std::string ptx(size, '\0');
+        rtc->nvrtcGetPTX(prog, &ptx[0]);
         rtc->nvrtcDestroyProgram(&prog);
-        return fail(CLODE_ERR_BUILD, "nvrtcGetCUBINSize failed");
+        while (!ptx.empty() && ptx.back() == '\0') ptx.pop_back();
+        int replaced = 0;
+        ptx = rewrite_constant_divisions(ptx, &replaced);
+        int rc = assemble_ptx(ptx, cubin, log);
+        if (rc) return rc;
+        log += "\n(ptx pass: " + std::to_string(replaced) + " divisions by a literal constant rewritten)";
+    } else {
+        r = rtc->nvrtcGetCUBINSize(prog, &size);
+        if (r != NVRTC_SUCCESS || size == 0) {
+            rtc->nvrtcDestroyProgram(&prog);
+            return fail(CLODE_ERR_BUILD, "nvrtcGetCUBINSize failed");
+        }
+        cubin.resize(size);
+        rtc->nvrtcGetCUBIN(prog, cubin.data());
+        rtc->nvrtcDestroyProgram(&prog);
     }
-    cubin.resize(size);
-    rtc->nvrtcGetCUBIN(prog, cubin.data());
-    rtc->nvrtcDestroyProgram(&prog);
     if (use_cache) {
         mkdir(dir.c_str(), 0755);
         std::string tmp = path + ".tmp" + std::to_string((long)getpid());
@@ -672,7 +791,7 @@ int clode_sim_destroy(clode_sim *s)
 }
 
 // load one compiled module into the simulation object and look up its kernels
-static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<char> &cubin, int *max_local_bytes)
+static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<char> &cubin, int local_bytes[4])
 {
     int rc;
     if (s->module) {
@@ -696,14 +815,12 @@ static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<
     if (spec.kernels & CLODE_KERNEL_TRAJECTORY) {
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_trajectory, s->module, "clode_trajectory"), "clode_trajectory"))) return rc;
     }
-    int worst = 0;
-    CUfunction hot[] = {s->k_transient, s->k_features, s->k_trajectory};
-    for (CUfunction f : hot) {
-        int local = 0;
-        if (f) s->d->cuFuncGetAttribute(&local, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
-        worst = std::max(worst, local);
+    // per-thread local memory (spills + stack) of each time-loop kernel; -1 = kernel not in this program
+    CUfunction loops[4] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory};
+    for (int k = 0; k < 4; ++k) {
+        local_bytes[k] = -1;
+        if (loops[k]) s->d->cuFuncGetAttribute(&local_bytes[k], CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, loops[k]);
     }
-    *max_local_bytes = worst;
     return CLODE_OK;
 }
 
@@ -727,6 +844,11 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
     //   4 blocks/SM (<= 128 regs) if spills <= 1 KiB/thread  (C3 lactotroph thresh2: +13 %, C4 seuler: +34 %)
     //   3 blocks/SM if spills <= 2 KiB, else 2, else 1.
     // Every variant lands in the cubin cache, so the search is paid once per program.
+    // The rule is applied PER KERNEL: every candidate is compiled with one target for all kernels, each kernel
+    // keeps the highest target at which it meets the spill limit, and if the kernels end up with different
+    // targets the program is compiled once more with individual __launch_bounds__ (C3: initializeObserver's
+    // warm-up pass carries four extents and fits 96 registers, the features pass carries the thresh2 record
+    // and needs 128).
     std::vector<int> candidates;
     std::vector<int> spill_limit;
     if (desc->min_blocks_per_sm > 0) {
@@ -747,15 +869,45 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
         }
     }
     std::string log;
+    int chosen[4] = {0, 0, 0, 0};
+    int local[4] = {-1, -1, -1, -1};
     for (size_t k = 0; k < candidates.size(); ++k) {
         spec.min_blocks = candidates[k];
         std::vector<char> cubin;
         rc = compile_spec(spec, cubin, log);
         s->build_log = rc ? g_error : log;
         if (rc) return rc;
-        int spilled = 0;
-        if ((rc = load_module(s, spec, cubin, &spilled))) return rc;
-        if (spilled <= spill_limit[k] || k + 1 == candidates.size()) break;
+        if ((rc = load_module(s, spec, cubin, local))) return rc;
+        if (spec.observer != 4 && spec.observer != 5) local[1] = -1; // one-pass observers: no time loop in initializeObserver
+        bool open = false;
+        for (int j = 0; j < 4; ++j) {
+            if (local[j] < 0 || chosen[j] > 0) continue;
+            if (local[j] <= spill_limit[k] || k + 1 == candidates.size()) chosen[j] = candidates[k];
+            else open = true;
+        }
+        if (!open) break;
+    }
+    {
+        // the module now loaded was compiled with spec.min_blocks for every kernel: recompile if a kernel settled higher
+        // (CLODE_KERNEL_MIN_BLOCKS="t,i,f,j" overrides the choice, for sweeps)
+        if (const char *env = std::getenv("CLODE_KERNEL_MIN_BLOCKS")) {
+            int v[4] = {0, 0, 0, 0};
+            if (std::sscanf(env, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+                for (int j = 0; j < 4; ++j)
+                    if (v[j] > 0 && local[j] >= 0) chosen[j] = v[j];
+        }
+        bool mixed = false;
+        for (int j = 0; j < 4; ++j) {
+            spec.kernel_min_blocks[j] = chosen[j];
+            mixed = mixed || (chosen[j] > 0 && chosen[j] != spec.min_blocks);
+        }
+        if (mixed) {
+            std::vector<char> cubin;
+            rc = compile_spec(spec, cubin, log);
+            s->build_log = rc ? g_error : log;
+            if (rc) return rc;
+            if ((rc = load_module(s, spec, cubin, local))) return rc;
+        }
     }
     if (spec.kernels & CLODE_KERNEL_FEATURES) {
         // ask the module how many observer-state rows it needs

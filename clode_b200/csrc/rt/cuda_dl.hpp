@@ -107,6 +107,50 @@ struct NvrtcApi {
     }
 };
 
+// nvJitLink: PTX -> sm_100a cubin without a GPU (the same ptxas NVRTC embeds).  Used when the runtime
+// post-processes the PTX of a program (constant-divisor rewrite, clode_rt.cpp).  The library exports its entry
+// points under versioned names (__nvJitLinkCreate_12_0 ... _12_9); the _12_0 names exist in every 12.x release.
+struct JitLinkApi {
+    typedef struct nvJitLink *Handle;
+    int (*Create)(Handle *, unsigned int, const char **) = nullptr;
+    int (*Destroy)(Handle *) = nullptr;
+    int (*AddData)(Handle, int /* nvJitLinkInputType */, const void *, size_t, const char *) = nullptr;
+    int (*Complete)(Handle) = nullptr;
+    int (*GetLinkedCubinSize)(Handle, size_t *) = nullptr;
+    int (*GetLinkedCubin)(Handle, void *) = nullptr;
+    int (*GetErrorLogSize)(Handle, size_t *) = nullptr;
+    int (*GetErrorLog)(Handle, char *) = nullptr;
+    enum { INPUT_PTX = 2 }; // NVJITLINK_INPUT_PTX (nvJitLink.h: NONE, CUBIN, PTX, ...)
+    void *handle = nullptr;
+    std::string error;
+
+    bool load()
+    {
+        const char *names[] = {"libnvJitLink.so.12", "/usr/local/cuda/lib64/libnvJitLink.so.12", "libnvJitLink.so",
+                               "/usr/local/cuda/lib64/libnvJitLink.so"};
+        for (const char *n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            error = std::string("cannot load nvJitLink (libnvJitLink.so.12): ") + dlerror();
+            return false;
+        }
+#define X(member, sym)                                                         \
+    member = reinterpret_cast<decltype(member)>(dlsym(handle, sym));           \
+    if (!member) {                                                             \
+        error = std::string("nvJitLink lacks symbol ") + sym;                  \
+        return false;                                                          \
+    }
+        X(Create, "__nvJitLinkCreate_12_0") X(Destroy, "__nvJitLinkDestroy_12_0") X(AddData, "__nvJitLinkAddData_12_0")
+        X(Complete, "__nvJitLinkComplete_12_0") X(GetLinkedCubinSize, "__nvJitLinkGetLinkedCubinSize_12_0")
+        X(GetLinkedCubin, "__nvJitLinkGetLinkedCubin_12_0") X(GetErrorLogSize, "__nvJitLinkGetErrorLogSize_12_0")
+        X(GetErrorLog, "__nvJitLinkGetErrorLog_12_0")
+#undef X
+        return true;
+    }
+};
+
 // lazily-initialised singletons; nullptr + message on failure
 inline DriverApi *driver(std::string *why = nullptr)
 {
@@ -121,6 +165,16 @@ inline DriverApi *driver(std::string *why = nullptr)
 inline NvrtcApi *nvrtc(std::string *why = nullptr)
 {
     static NvrtcApi api;
+    static bool ok = false;
+    static std::once_flag once;
+    std::call_once(once, [] { ok = api.load(); });
+    if (!ok && why) *why = api.error;
+    return ok ? &api : nullptr;
+}
+
+inline JitLinkApi *jitlink(std::string *why = nullptr)
+{
+    static JitLinkApi api;
     static bool ok = false;
     static std::once_flag once;
     std::call_once(once, [] { ok = api.load(); });

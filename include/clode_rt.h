@@ -89,6 +89,15 @@ typedef struct clode_program_desc {
                                  (fixed-step methods); 0: per-thread coalesced stores                     */
     int observer_in_shared;   /* 1: observer state in a per-thread shared-memory slot instead of registers
                                  (for the fat observers); 0: registers                                    */
+    int ieee_constant_division; /* 0 (default, ignored when bit_exact): `x / literal` in the program's PTX is
+                                 evaluated as q = x*y, q + (x - c*q)*y with y = RN(1/c) from the host — the
+                                 correctly rounded quotient for |x| in [2^-511, 2^512), one ulp outside —
+                                 instead of ptxas' generic sequence, which Newton-refines the literal's
+                                 reciprocal at run time; 1: leave every division to ptxas              */
+    int library_exp;          /* 0 (default): in production double builds exp() is the engine's table + degree-5
+                                 polynomial (device/fast_exp.cuh, <= 0.52 ulp, 11 FP64 instructions); 1: CUDA's
+                                 libdevice exp (1 ulp, 15 FP64 instructions + coefficient moves).  Ignored by
+                                 bit_exact and single-precision builds                                      */
 } clode_program_desc;
 
 /* compile only (no GPU needed): returns malloc'd cubin + log; caller frees with clode_free */

@@ -1,0 +1,64 @@
+// Host check of clode_b200/csrc/device/fast_exp.cuh: the device function compiled as host C++ (same text, same
+// IEEE fma) against the 80-bit expl of the host.  Driven by tests/test_fast_exp.py.
+// Build: g++ -O2 -march=x86-64-v3 -ffp-contract=off
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__ static const
+struct double2 { double x, y; };
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline int __double2hiint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int __double2loint(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(uint32_t)b; }
+static inline double __hiloint2double(int hi, int lo)
+{
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x; std::memcpy(&x, &b, 8); return x;
+}
+using std::fma;
+using std::exp;
+#include "fast_exp.cuh"
+
+static double ulps(double y, double x)
+{
+    const long double ref = expl((long double)x);
+    if (std::isinf((double)ref) || ref == 0.0L) return y == (double)ref ? 0.0 : 1e9;
+    int e;
+    frexpl(ref, &e);
+    if (e < -1021) e = -1021; // subnormal results: spacing 2^-1074
+    return (double)(fabsl((long double)y - ref) / ldexpl(1.0L, e - 53));
+}
+
+int main(int argc, char **argv)
+{
+    const long count = argc > 1 ? std::atol(argv[1]) : 1000000;
+    std::mt19937_64 g(7);
+    const double ranges[][2] = {{-1, 1}, {-10, 10}, {-100, 100}, {-707.9, 707.9}, {-0.01, 0.01}, {-40, 5}, {-750, 720}};
+    double worst = 0;
+    for (auto &rg : ranges) {
+        std::uniform_real_distribution<double> d(rg[0], rg[1]);
+        double w = 0;
+        for (long i = 0; i < count; ++i) {
+            const double x = d(g);
+            const double err = ulps(clode_fast_exp(x), x);
+            if (err > w) w = err;
+        }
+        std::printf("range [%g, %g]: max error %.4f ulp\n", rg[0], rg[1], w);
+        if (w > worst) worst = w;
+    }
+    // special values take the library path
+    const double specials[] = {0.0, -0.0, 708.0, -708.0, 709.78, 710.0, -745.0, -746.0, INFINITY, -INFINITY, 0x1p-1074, 1e-300};
+    int bad = 0;
+    for (double x : specials)
+        if (ulps(clode_fast_exp(x), x) > 1.0) { std::printf("special %a wrong\n", x); ++bad; }
+    if (!std::isnan(clode_fast_exp(NAN))) { std::printf("NaN not propagated\n"); ++bad; }
+    if (clode_fast_exp(0.0) != 1.0) { std::printf("exp(0) != 1\n"); ++bad; }
+    std::printf("worst=%.4f bad=%d\n", worst, bad);
+    return (worst < 0.53 && bad == 0) ? 0 : 1;
+}
