@@ -3,13 +3,15 @@
 // libdevice's exp is a degree-11 polynomial after a ln2 range reduction: 15 FP64-pipe instructions on one
 // dependent chain plus ~24 moves that materialise its coefficients — and a gating-variable model calls it three to
 // eight times per right-hand side (samples/lactotroph.cl: 3, examples/chay_keizer.cl: 8), i.e. up to 32 times per RK4
-// step.  This one reduces by ln2/128 instead, looks 2^(j/128) up in a 1 KiB table (read-only data path, L1-resident)
-// and needs a degree-5 polynomial: 11 FP64-pipe instructions, chain depth 9.
+// step.  This one reduces by ln2/128 instead, looks 2^(j/128) up in a 2 KiB table and needs a degree-5 polynomial:
+// 11 FP64-pipe instructions, chain depth 9.  The table is staged in SHARED memory at kernel entry: read through
+// L1 (__ldg) it shares the cache with the local-memory spills of the fat-observer kernels, which evict it — C3
+// (lactotroph, thresh2, 600 B of spills per thread) was 2 % slower with the L1 table than with libdevice's exp.
 //     x = (128 m + j) ln2/128 + r,  |r| <= ln2/256:   exp(x) = 2^m * T[j] * (1 + p(r)),  p(r) = r + r^2/2 + ... + r^5/120
 // The table entry is carried as hi + lo, so the only full rounding is the last addition: error <= 0.52 ulp measured
 // over 2e7 arguments against 80-bit expl (tests/test_fast_exp.py) — CUDA documents 1 ulp for its own exp, OpenCL C
-// allows 3.  Arguments outside |x| < 708 (overflow, subnormal results,
-// Inf, NaN) go to the library function.
+// allows 3.  Overflow, subnormal results (rounded twice, <= 1 ulp of the subnormal grid), Inf and NaN take an inline
+// branch, as in libdevice; there is no call.
 #ifndef CLODE_FAST_EXP_CUH
 #define CLODE_FAST_EXP_CUH
 
@@ -81,7 +83,19 @@ __device__ const double2 clode_exp2_table[128] = {
     {0x1.fa7c1819e90d8p+0, 0x1.74853f3a5931ep-55}, {0x1.fd3c22b8f71f1p+0, 0x1.2eb74966579e7p-57},
 };
 
-static __device__ __noinline__ double clode_exp_edge(const double x) { return exp(x); }
+#ifndef CLODE_EXP_HOST_CHECK
+__shared__ double2 clode_exp2_smem[128];
+// every thread of the block, before any thread leaves the kernel
+static __device__ __forceinline__ void clode_stage_exp_table()
+{
+    for (unsigned int j = threadIdx.x; j < 128u; j += blockDim.x)
+        clode_exp2_smem[j] = clode_exp2_table[j];
+    __syncthreads();
+}
+#define CLODE_EXP2_ENTRY(j) clode_exp2_smem[j]
+#else
+#define CLODE_EXP2_ENTRY(j) clode_exp2_table[j]
+#endif
 
 // Scalars in the constant bank: each is then a c[bank][offset] operand of the DFMA that uses it; as literals every
 // call site re-materialises them with two UMOVs apiece inside the time loop (cf. the RK tableaux, steppers.cuh).
@@ -94,8 +108,6 @@ __constant__ double clode_exp_c[8] = {
 
 static __device__ __forceinline__ double clode_fast_exp(const double x)
 {
-    // |x| < 708 on the high word (NaN and Inf compare above): everything else is the library's business
-    if ((__double2hiint(x) & 0x7fffffff) >= 0x40862000) return clode_exp_edge(x);
     const double *c = clode_exp_c;
     const double kf = fma(x, c[0], c[1]);
     const int k = __double2loint(kf);
@@ -105,8 +117,18 @@ static __device__ __forceinline__ double clode_fast_exp(const double x)
     const double r2 = r * r;
     double p = fma(r, fma(r, fma(r, c[4], c[5]), c[6]), c[7]);
     p = fma(r2, p, r);
-    const double2 t = __ldg(&clode_exp2_table[k & 127]);
-    const double y = t.x + fma(t.x, p, t.y);
-    return __hiloint2double(__double2hiint(y) + ((k >> 7) << 20), __double2loint(y)); // * 2^m: |x| < 708 keeps it normal
+    const double2 t = CLODE_EXP2_ENTRY(k & 127);
+    const double y = t.x + fma(t.x, p, t.y); // in [1, 2.01)
+    const int m = k >> 7;
+    const int hi_abs = __double2hiint(x) & 0x7fffffff;
+    if (hi_abs < 0x40862000) // |x| < 708: y * 2^m is a normal number, add m to the exponent field
+        return __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+    // rare: overflow, subnormal results, Inf, NaN (the same cases libdevice branches on)
+    if (hi_abs >= 0x40900000) // |x| >= 1024, Inf or NaN
+        return x != x ? x + x : (x > 0.0 ? __hiloint2double(0x7ff00000, 0) : 0.0);
+    // 708 <= |x| < 1024: two exact power-of-two factors; the second multiplication rounds once (to a subnormal,
+    // zero or infinity where that is the answer)
+    const int m1 = m >> 1;
+    return y * __hiloint2double((1023 + m1) << 20, 0) * __hiloint2double((1023 + m - m1) << 20, 0);
 }
 #endif // CLODE_FAST_EXP_CUH

@@ -75,6 +75,14 @@ struct KernelArgs {
     unsigned int *rs_uint;         // [3][n]: accepted steps so far, rows stored so far, variate cached?
     unsigned int *chunk_flags;     // [2]: an instance is still live after this launch / highest row index stored
     unsigned int row_begin, row_end, resume; // monolithic launch: 0, 0xffffffff, 0
+    // Block -> chunk of CLODE_BLOCK consecutive instances.  Blocks are dispatched in index order, so when the cost of
+    // an instance grows along the ensemble (a sorted parameter sweep) the most expensive warps start last and the
+    // device drains behind them; walking the ensemble backwards puts the cheap ones last (longest-processing-time
+    // first).  0: forward, 1: reverse, 2: decide from cost_in — the accepted steps the previous launch on this
+    // ensemble spent in the lower / upper half of the index range (every kernel accumulates them into cost_out).
+    unsigned int block_order;
+    const unsigned long long *cost_in; // [2] or null
+    unsigned long long *cost_out;      // [2] or null
 };
 
 extern "C" __constant__ KernelArgs clode_args;
@@ -180,12 +188,32 @@ CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams
 template <class Job> CLODE_DEV void run_ensemble(const KernelArgs &a, Job &job)
 {
 #ifndef CLODE_WORK_QUEUE
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool reverse = a.block_order == 1u;
+#ifndef __CUDACC_EMU__
+    if (a.block_order == 2u) {
+        const unsigned long long lower = a.cost_in[0], upper = a.cost_in[1];
+        reverse = upper > lower + (lower >> 5); // 3 % hysteresis
+    }
+#endif
+    const size_t chunk = reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const size_t i = chunk * (size_t)blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     job.begin(i);
     while (job.live())
         job.attempt();
     job.end(i);
+#ifndef __CUDACC_EMU__
+    if (a.cost_out) { // one atomic per warp and half
+        const unsigned int mask = __activemask();
+        const bool in_upper = 2 * i >= a.n;
+        const unsigned int s = min(job.step, 1u << 26);
+        const unsigned int lo = __reduce_add_sync(mask, in_upper ? 0u : s), hi = __reduce_add_sync(mask, in_upper ? s : 0u);
+        if ((threadIdx.x & 31u) == (unsigned int)(__ffs(mask) - 1)) {
+            if (lo) atomicAdd(a.cost_out, (unsigned long long)lo);
+            if (hi) atomicAdd(a.cost_out + 1, (unsigned long long)hi);
+        }
+    }
+#endif
 #else
     const unsigned int FULL = 0xffffffffu;
     const unsigned int lane = threadIdx.x & 31u;
@@ -240,6 +268,7 @@ struct TransientJob {
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRANSIENT)
 clode_transient()
 {
+    CLODE_KERNEL_PROLOGUE();
     TransientJob job(clode_args);
     run_ensemble(clode_args, job);
 }
@@ -330,6 +359,7 @@ struct WarmupJob {
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_INIT)
 clode_initialize_observer()
 {
+    CLODE_KERNEL_PROLOGUE();
     WarmupJob job(clode_args);
     run_ensemble(clode_args, job);
 }
@@ -395,6 +425,7 @@ struct FeaturesJob {
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_FEATURES)
 clode_features()
 {
+    CLODE_KERNEL_PROLOGUE();
     FeaturesJob job(clode_args);
     run_ensemble(clode_args, job);
 }
@@ -577,6 +608,7 @@ CLODE_DEV void tile_flush(realtype (*tile)[CLODE_BLOCK], const KernelArgs &a, co
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRAJECTORY)
 clode_trajectory()
 {
+    CLODE_KERNEL_PROLOGUE();
     const KernelArgs &a = clode_args;
     __shared__ __align__(128) realtype tile[2][TRAJ_LINES][CLODE_BLOCK];
     const size_t base = blockIdx.x * (size_t)blockDim.x;
@@ -631,6 +663,7 @@ clode_trajectory()
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRAJECTORY)
 clode_trajectory()
 {
+    CLODE_KERNEL_PROLOGUE();
     TrajectoryJob job(clode_args);
     run_ensemble(clode_args, job);
 }

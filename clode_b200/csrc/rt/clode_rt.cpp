@@ -386,6 +386,8 @@ struct KernelArgs {
     CUdeviceptr x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
     CUdeviceptr rs_real, rs_uint, chunk_flags;
     unsigned int row_begin, row_end, resume;
+    unsigned int block_order;
+    CUdeviceptr cost_in, cost_out;
 };
 
 std::string cu_error(DriverApi *d, CUresult r)
@@ -426,6 +428,7 @@ struct clode_sim {
     size_t n = 0;
     size_t real_size = 8;
     Buffer x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
+    Buffer cost; // 2 x 2 u64: accepted steps in the lower / upper half of the ensemble (block_order auto)
     size_t tr_rows = 0; // allocated trajectory rows (max_store + 1)
     // streamed trajectory: two chunk buffer sets (one integrates while the other is copied out) + resume state
     struct Chunk { Buffer t, x, dx, aux; } chunk[2];
@@ -493,7 +496,7 @@ struct clode_sim {
 
     void free_ensemble()
     {
-        Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue,
+        Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue, &cost,
                          &chunk[0].t, &chunk[0].x, &chunk[0].dx, &chunk[0].aux, &chunk[1].t, &chunk[1].x, &chunk[1].dx, &chunk[1].aux,
                          &rs_real, &rs_uint, &chunk_flags};
         for (Buffer *b : all) release(*b);
@@ -559,7 +562,20 @@ struct clode_sim {
         return launch_with(f, args(), what, first, last, blocking);
     }
 
-    int launch_with(CUfunction f, const KernelArgs &a, const char *what, bool first, bool last, bool blocking = true)
+    // Block -> chunk mapping (KernelArgs::block_order): forward, reverse, or — the default — decided on the device
+    // from the step counts the previous launch on this ensemble left in `cost` (two slots of two counters, used
+    // alternately as input and output).  CLODE_BLOCK_ORDER=forward|reverse|auto overrides.
+    int cost_slot = 0;
+    unsigned block_order_mode() const
+    {
+        const char *env = std::getenv("CLODE_BLOCK_ORDER");
+        if (spec.work_queue) return 0;
+        if (env && std::strcmp(env, "forward") == 0) return 0;
+        if (env && std::strcmp(env, "reverse") == 0) return 1;
+        return 2;
+    }
+
+    int launch_with(CUfunction f, const KernelArgs &a_in, const char *what, bool first, bool last, bool blocking = true)
     {
         if (!f) return fail(CLODE_ERR_STATE, std::string(what) + ": kernel not built");
         if (n == 0) return fail(CLODE_ERR_STATE, std::string(what) + ": no problem data set (nPts == 0)");
@@ -569,6 +585,18 @@ struct clode_sim {
         }
         unsigned grid = 1;
         if ((rc = grid_for(f, grid))) return rc;
+        KernelArgs a = a_in;
+        a.block_order = block_order_mode();
+        // initializeObserver of a one-pass observer has no time loop: it neither uses nor replaces the history
+        if (a.block_order == 2 && f == k_init && !two_pass) a.block_order = 0;
+        if (a.block_order == 2 && cost.ptr) {
+            a.cost_in = cost.ptr + 16 * cost_slot;
+            a.cost_out = cost.ptr + 16 * (1 - cost_slot);
+            if ((rc = cu(d->cuMemsetD8Async(a.cost_out, 0, 16, stream), "reset cost counters"))) return rc;
+            cost_slot ^= 1;
+        } else if (a.block_order == 2) {
+            a.block_order = 0;
+        }
         // arguments go to the module's __constant__ block, ordered in-stream before the launch
         // (pageable source: the driver stages the bytes before cuMemcpyHtoDAsync returns)
         if ((rc = cu(d->cuMemcpyHtoDAsync(args_symbol, &a, sizeof a, stream), "upload kernel arguments"))) return rc;
@@ -964,6 +992,9 @@ int clode_sim_set_npts(clode_sim *s, size_t n_pts, double fill_dt)
         if ((rc = s->alloc(s->tf, rs * n_pts, "tf"))) return rc;
         if ((rc = s->alloc(s->steps, 4 * n_pts, "steps"))) return rc;
         if ((rc = s->alloc(s->queue, 8, "queue"))) return rc;
+        if ((rc = s->alloc(s->cost, 32, "cost counters"))) return rc;
+        if ((rc = s->cu(s->d->cuMemsetD8Async(s->cost.ptr, 0, 32, s->stream), "memset cost counters"))) return rc; // new ensemble: forward
+        s->cost_slot = 0;
         if (n_pts) {
             if ((rc = s->cu(s->d->cuMemsetD8Async(s->rng.ptr, 0, s->rng.bytes, s->stream), "memset rng"))) return rc;
             if ((rc = s->cu(s->d->cuMemsetD8Async(s->xf.ptr, 0, s->xf.bytes, s->stream), "memset xf"))) return rc;

@@ -30,3 +30,28 @@ def golden():
     import numpy as np
 
     return np.load(os.path.join(HERE, "golden", "golden_ref.npz"))
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _precompile_only():
+    """CLODE_PRECOMPILE=1 python -m pytest tests -m gpu  (on a machine WITHOUT a GPU): every program a GPU test
+    would build through clode_b200._rt.Sim is compiled into the cubin cache instead (the first occupancy
+    candidates the runtime would try) and the test is skipped — the GPU box then finds the cubins and skips the JIT."""
+    if os.environ.get("CLODE_PRECOMPILE") != "1":
+        yield
+        return
+    import dataclasses
+
+    from clode_b200 import _rt
+
+    def init(self, prog, device=0):
+        self._h = None
+        blocks = [prog.min_blocks_per_sm] if prog.min_blocks_per_sm else ([8, 5, 4] if prog.single_precision else [5, 4])
+        for m in blocks:
+            _rt.compile_program(dataclasses.replace(prog, min_blocks_per_sm=m))
+        pytest.skip("precompiled")
+
+    original = _rt.Sim.__init__
+    _rt.Sim.__init__ = init
+    yield
+    _rt.Sim.__init__ = original

@@ -16,7 +16,7 @@
 #define __restrict__
 
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local emu_dim3 blockIdx, blockDim, threadIdx;
+static thread_local emu_dim3 blockIdx, blockDim, threadIdx, gridDim;
 
 struct float2 { float x, y; };
 struct float3 { float x, y, z; };

@@ -39,7 +39,8 @@ class KernelArgs(ctypes.Structure):
     ] + [(k, ctypes.c_void_p) for k in ("x0", "pars", "xf", "rng", "dt", "tf", "steps", "od_real", "od_uint", "F",
                                         "tr_t", "tr_x", "tr_dx", "tr_aux", "n_stored", "queue",
                                         "rs_real", "rs_uint", "chunk_flags")] + [
-        ("row_begin", ctypes.c_uint), ("row_end", ctypes.c_uint), ("resume", ctypes.c_uint)]
+        ("row_begin", ctypes.c_uint), ("row_end", ctypes.c_uint), ("resume", ctypes.c_uint), ("block_order", ctypes.c_uint),
+        ("cost_in", ctypes.c_void_p), ("cost_out", ctypes.c_void_p)]
 
 
 def _ptr(a):
@@ -97,6 +98,7 @@ class EmuLib:
             a.op_eps_dx = op.eps_dx
         a.n = n
         a.row_begin, a.row_end, a.resume = 0, 0xFFFFFFFF, 0
+        a.block_order = getattr(self, "block_order", 0)
         for k, v in bufs.items():
             setattr(a, k, _ptr(v) if v is not None else None)
         return a

@@ -25,6 +25,7 @@ static void run(void (*kernel)(), const KernelArgs *a)
     const unsigned block = CLODE_BLOCK;
     const unsigned grid = (unsigned)((a->n + block - 1) / block);
     blockDim.x = block;
+    gridDim.x = grid;
     for (unsigned b = 0; b < grid; ++b)
         for (unsigned t = 0; t < block; ++t) {
             blockIdx.x = b;

@@ -11,6 +11,7 @@
 #define __device__
 #define __forceinline__ inline
 #define __noinline__
+#define CLODE_EXP_HOST_CHECK
 #define __constant__ static const
 struct double2 { double x, y; };
 template <class T> static inline T __ldg(const T *p) { return *p; }
@@ -22,7 +23,7 @@ static inline double __hiloint2double(int hi, int lo)
     double x; std::memcpy(&x, &b, 8); return x;
 }
 using std::fma;
-using std::exp;
+
 #include "fast_exp.cuh"
 
 static double ulps(double y, double x)
@@ -50,7 +51,10 @@ int main(int argc, char **argv)
             if (err > w) w = err;
         }
         std::printf("range [%g, %g]: max error %.4f ulp\n", rg[0], rg[1], w);
-        if (w > worst) worst = w;
+        // results that are subnormal are rounded twice (once to 53 bits, once to the subnormal grid): up to 1 ulp there
+        const bool edge = rg[0] < -708.0;
+        if (edge ? w > 1.0 : w > 0.53) worst = 9.0;
+        if (!edge && w > worst) worst = w;
     }
     // special values take the library path
     const double specials[] = {0.0, -0.0, 708.0, -708.0, 709.78, 710.0, -745.0, -746.0, INFINITY, -INFINITY, 0x1p-1074, 1e-300};

@@ -9,7 +9,7 @@ import pytest
 from emu import EmuLib
 from golden_cases import CASES, case_inputs
 from oracle import restate
-from oracle.common import Config, Observer, Solver
+from oracle.common import Config, Observer, Solver, seed_states
 from problems import ensemble
 from util import assert_bit_equal, run_oracle
 
@@ -115,3 +115,19 @@ def test_streamed_trajectory_matches_single_launch(model, stepper, dt, nout, max
         parts = lib.trajectory_stream(ts, x0, pars, sp, d, rng, chunk_rows)
         _streamed_equals_whole(whole, parts, n, widths, f"{model}/{stepper} chunk_rows={chunk_rows}")
         assert parts["launches"] <= -(-(max_store + 1) // min(chunk_rows, max_store + 1))
+
+
+@pytest.mark.parametrize("order", [1])
+def test_block_order_only_permutes_the_schedule(order):
+    """KernelArgs::block_order = 1 walks the ensemble backwards: every instance is still integrated exactly once, so all outputs are unchanged (ragged n: 9 blocks, last one partial)"""
+    cfg = Config("lorenz63", "dopri5", "basic", math="pm")
+    lib = EmuLib(cfg)
+    n = 8 * 128 + 37
+    ts, x0, pars = ensemble("lorenz63", n)
+    sp = Solver(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, max_steps=100000)
+    dt, rng = np.full(n, sp.dt), seed_states(1, n)
+    want = lib.features((0.0, 2.0), x0, pars, sp, Observer(), dt, rng)
+    lib.block_order = order
+    got = lib.features((0.0, 2.0), x0, pars, sp, Observer(), dt, rng)
+    lib.block_order = 0
+    assert_bit_equal(got, want, f"block_order={order}")

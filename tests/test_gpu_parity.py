@@ -291,6 +291,30 @@ def test_cuda_abi_error_behaviour(rt):
 
 # ----------------------------------------------------------------------------------------------
 # persistent-thread work queue with per-lane refill: results must not depend on which lane ran what
+@pytest.mark.parametrize("model,stepper,observer", [("lorenz63", "dopri5", "basic"), ("lactotroph", "bs23", "thresh2")])
+def test_cuda_block_order_does_not_change_results(rt, model, stepper, observer, monkeypatch):
+    """the block -> chunk mapping (forward / reverse / decided from the previous launch's step counts) is a schedule:
+    every output is bit-identical, on the first call (no history) and on a repeated call (history from the first)"""
+    n = 3000 + 7  # ragged: the last block is partial
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[1] / 8)
+    sp = Solver(dt=0.1, dtmax=10.0, abstol=1e-6, reltol=1e-4, max_steps=200000)
+    op = Observer(max_event_count=8, x_up_threshold=0.3, x_down_threshold=0.2)
+    results = {}
+    for order in ("forward", "reverse", "auto"):
+        monkeypatch.setenv("CLODE_BLOCK_ORDER", order)
+        g = GpuRun(rt, model, stepper, observer, bit_exact=True)
+        g.setup(ts, x0, pars, sp, op, seed=2)
+        first = g.features()
+        g.setup(ts, x0, pars, sp, op, seed=2)   # same ensemble again: `auto` now has the first call's step counts
+        second = g.features()
+        g.close()
+        assert_bit_equal(second, first, f"{order}: repeated call")
+        results[order] = first
+    assert_bit_equal(results["reverse"], results["forward"], "reverse vs forward")
+    assert_bit_equal(results["auto"], results["forward"], "auto vs forward")
+
+
 @pytest.mark.parametrize("model,stepper,observer,kind", [
     ("lorenz63", "dopri5", "localmax", "features"),
     ("lactotroph", "bs23", "thresh2", "features"),   # two-pass: the warm-up kernel also runs from the queue
