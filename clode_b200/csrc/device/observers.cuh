@@ -112,9 +112,34 @@ CLODE_DEV int argmin3(realtype a, realtype b, realtype c, realtype &best)
 CLODE_DEV realtype pick3(const realtype v[3], int at) { return at == 0 ? v[0] : (at == 1 ? v[1] : v[2]); }
 
 // extents and means of all variables, slopes and aux variables
+//
+// CLODE_EXT_SMEM: the 5 nVar + 3 nAux values live in shared memory, field-major [field][thread] (consecutive threads,
+// consecutive words: conflict-free), instead of registers.  They are touched once per ACCEPTED step, outside the RK
+// stages, and the extremes are almost never written after the first oscillation (a load and a compare per step), while
+// in registers they cost the fat observers 46 registers (nVar = 4) that the trial step then has to spill around:
+// C3's features kernel executed 72 local loads + 51 local stores per attempt before this.  The accesses are volatile
+// so that the compiler does not promote the words back into registers for the whole time loop.
+#if defined(CLODE_EXT_SMEM) && !defined(CLODE_OBS_SMEM) && !defined(__CUDACC_EMU__)
+#define CLODE_EXT_IN_SMEM 1
+__shared__ volatile realtype clode_ext_smem[5 * NV + 3 * NA_][CLODE_BLOCK];
+template <int BASE, int STRIDE> struct ExtField {
+    __device__ __forceinline__ volatile realtype &operator[](int j) const { return clode_ext_smem[BASE + STRIDE * j][threadIdx.x]; }
+};
+CLODE_DEV void ext_max(volatile realtype &m, const realtype v) { if (v > m) m = v; } // == max_nn(v, m), stored only on change
+CLODE_DEV void ext_min(volatile realtype &m, const realtype v) { if (v < m) m = v; }
+#else
+#define CLODE_EXT_IN_SMEM 0
+CLODE_DEV void ext_max(realtype &m, const realtype v) { m = max_nn(v, m); }
+CLODE_DEV void ext_min(realtype &m, const realtype v) { m = min_nn(v, m); }
+#endif
 struct Extents {
+#if CLODE_EXT_IN_SMEM
+    ExtField<0, 5> xmax; ExtField<1, 5> xmin; ExtField<2, 5> xmean; ExtField<3, 5> dxmax; ExtField<4, 5> dxmin;
+    ExtField<5 * NV + 0, 3> amax; ExtField<5 * NV + 1, 3> amin; ExtField<5 * NV + 2, 3> amean;
+#else
     realtype xmax[NV], xmin[NV], xmean[NV], dxmax[NV], dxmin[NV];
     realtype amax[NA_], amin[NA_], amean[NA_];
+#endif
     __device__ __forceinline__ void reset()
     {
 #pragma unroll
@@ -130,16 +155,16 @@ struct Extents {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            xmax[j] = max_nn(I.x[j], xmax[j]);
-            xmin[j] = min_nn(I.x[j], xmin[j]);
+            ext_max(xmax[j], I.x[j]);
+            ext_min(xmin[j], I.x[j]);
             xmean[j] = mean_time(xmean[j], I.x[j], w);
-            dxmax[j] = max_nn(I.k1[j], dxmax[j]);
-            dxmin[j] = min_nn(I.k1[j], dxmin[j]);
+            ext_max(dxmax[j], I.k1[j]);
+            ext_min(dxmin[j], I.k1[j]);
         }
 #pragma unroll
         for (int j = 0; j < N_AUX; ++j) {
-            amax[j] = max_nn(I.aux[j], amax[j]);
-            amin[j] = min_nn(I.aux[j], amin[j]);
+            ext_max(amax[j], I.aux[j]);
+            ext_min(amin[j], I.aux[j]);
             amean[j] = mean_time(amean[j], I.aux[j], w);
         }
     }
@@ -148,9 +173,9 @@ struct Extents {
     {
 #if CLODE_INTEGRAL_MEANS
 #pragma unroll
-        for (int j = 0; j < NV; ++j) xmean[j] *= span;
+        for (int j = 0; j < NV; ++j) xmean[j] = xmean[j] * span;
 #pragma unroll
-        for (int j = 0; j < N_AUX; ++j) amean[j] *= span;
+        for (int j = 0; j < N_AUX; ++j) amean[j] = amean[j] * span;
 #endif
     }
     __device__ __forceinline__ void close_means(realtype span)
@@ -158,9 +183,9 @@ struct Extents {
 #if CLODE_INTEGRAL_MEANS
         if (span != ZERO) { // span == 0: nothing was ever accumulated (sums are 0, as the means were)
 #pragma unroll
-            for (int j = 0; j < NV; ++j) xmean[j] /= span;
+            for (int j = 0; j < NV; ++j) xmean[j] = xmean[j] / span;
 #pragma unroll
-            for (int j = 0; j < N_AUX; ++j) amean[j] /= span;
+            for (int j = 0; j < N_AUX; ++j) amean[j] = amean[j] / span;
         }
 #endif
     }
@@ -169,25 +194,34 @@ struct Extents {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            xmax[j] = max_nn(I.x[j], xmax[j]);
-            xmin[j] = min_nn(I.x[j], xmin[j]);
-            mean_count(&xmean[j], I.x[j], count);
-            dxmax[j] = max_nn(I.k1[j], dxmax[j]);
-            dxmin[j] = min_nn(I.k1[j], dxmin[j]);
+            ext_max(xmax[j], I.x[j]);
+            ext_min(xmin[j], I.x[j]);
+            { realtype m = xmean[j]; mean_count(&m, I.x[j], count); xmean[j] = m; }
+            ext_max(dxmax[j], I.k1[j]);
+            ext_min(dxmin[j], I.k1[j]);
         }
 #pragma unroll
         for (int j = 0; j < N_AUX; ++j) {
-            amax[j] = max_nn(I.aux[j], amax[j]);
-            amin[j] = min_nn(I.aux[j], amin[j]);
-            mean_count(&amean[j], I.aux[j], count);
+            ext_max(amax[j], I.aux[j]);
+            ext_min(amin[j], I.aux[j]);
+            { realtype m = amean[j]; mean_count(&m, I.aux[j], count); amean[j] = m; }
         }
+    }
+    // persistence visitor: through a temporary, so that it works for both placements
+    template <class V, class F> __device__ __forceinline__ static void visit_one(V &v, F &&field)
+    {
+        realtype tmp = field;
+        v(tmp);
+        field = tmp;
     }
     template <class V> __device__ __forceinline__ void visit(V &v)
     {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) { v(xmax[j]); v(xmin[j]); v(xmean[j]); v(dxmax[j]); v(dxmin[j]); }
+        for (int j = 0; j < NV; ++j) {
+            visit_one(v, xmax[j]); visit_one(v, xmin[j]); visit_one(v, xmean[j]); visit_one(v, dxmax[j]); visit_one(v, dxmin[j]);
+        }
 #pragma unroll
-        for (int j = 0; j < N_AUX; ++j) { v(amax[j]); v(amin[j]); v(amean[j]); }
+        for (int j = 0; j < N_AUX; ++j) { visit_one(v, amax[j]); visit_one(v, amin[j]); visit_one(v, amean[j]); }
     }
 };
 
@@ -554,8 +588,8 @@ struct Observer {
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            ext.xmax[j] = max_nn(I.x[j], ext.xmax[j]);
-            ext.xmin[j] = min_nn(I.x[j], ext.xmin[j]);
+            ext_max(ext.xmax[j], I.x[j]);
+            ext_min(ext.xmin[j], I.x[j]);
         }
     }
     __device__ __forceinline__ void arm(const Instance &, const ObserverParams &op)

@@ -213,9 +213,11 @@ inline bool extra(CLODEtrajectory &t, const std::string &cmd, int nlhs, mxArray 
 template <class T> void initializeAll(T &obj, int nrhs, const mxArray *prhs[])
 {
     if (nrhs < 6) mexErrMsgIdAndTxt("clODE:args", "initialize: expected tspan, x0, pars, solver-parameter struct");
+    // solver parameters first: the per-instance dt buffer is filled with sp.dt when the problem data fixes nPts and is
+    // not refilled by a later setSolverParams (reference semantics, CLODE.cpp:201-227, 382)
+    obj.setSolverParams(toSolverParams(prhs[5]));
     obj.setTspan(toVector(prhs[2]));
     obj.setProblemData(toVector(prhs[3]), toVector(prhs[4]));
-    obj.setSolverParams(toSolverParams(prhs[5]));
     if constexpr (std::is_same<T, CLODEfeatures>::value)
         if (nrhs > 6) obj.setObserverParams(toObserverParams(prhs[6]));
 }

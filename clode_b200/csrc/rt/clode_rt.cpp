@@ -80,6 +80,7 @@ struct ProgramSpec {
     int f_var = 0, e_var = 0, n_store = 0;
     int kernels = CLODE_KERNEL_TRANSIENT;
     bool bit_exact = false, work_queue = false, staged = false, obs_smem = false;
+    bool ext_smem = false;    // extents / means of the multi-variable observers in shared memory (observers.cuh)
     bool library_exp = false; // keep CUDA's exp in production double builds (default: device/fast_exp.cuh)
     bool const_div = true; // ptx_pass.hpp: divisions by literal constants without the Newton refinement of the literal
     int block = 128, min_blocks = 4;
@@ -110,6 +111,10 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.library_exp = d->library_exp != 0;
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
+    {
+        const char *env = std::getenv("CLODE_EXT_SMEM");
+        s.ext_smem = env && *env == '1' && (s.kernels & CLODE_KERNEL_FEATURES) && s.observer != 0 && !s.obs_smem;
+    }
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
     s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4; // 0 = chosen at build time (clode_sim_build)
@@ -149,6 +154,7 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
+    if (s.ext_smem) o.push_back("-DCLODE_EXT_SMEM");
     return o;
 }
 

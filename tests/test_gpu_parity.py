@@ -491,3 +491,31 @@ def test_cuda_observer_in_shared_memory_bit_exact(rt, model, stepper, observer):
     o2 = lib.features((ts[1], ts[1] + (ts[1] - ts[0])), o1["xf"], pars, sp, op, o1["dt"], o1["rng"], initialize=False)
     assert_bit_equal(r2, o2, "continued")
     g.close()
+
+
+@pytest.mark.parametrize("model,stepper,observer", [("lactotroph", "bs23", "thresh2"), ("lactotroph", "dopri5", "nhood2"),
+                                                    ("lorenz63", "dopri5", "localmax"), ("lactotroph", "rk4", "nhood1"),
+                                                    ("lorenz63", "bs23", "basicall")])
+def test_cuda_extents_in_shared_memory_bit_exact(rt, model, stepper, observer, monkeypatch):
+    """CLODE_EXT_SMEM=1: the per-variable extents / means of the multi-variable observers live in shared memory
+    (observers.cuh); placement only — every output is bit-identical to the oracle, also across a continued call"""
+    monkeypatch.setenv("CLODE_EXT_SMEM", "1")
+    n = 333
+    ts, x0, pars = ensemble(model, n)
+    ts = (ts[0], ts[1] / 4)
+    ns = 2 if observer in ("localmax", "nhood2", "thresh2") else 0
+    sp = Solver(dt=0.05 if stepper == "rk4" else 0.1, dtmax=10.0, abstol=1e-6, reltol=1e-4, max_steps=200000)
+    op = Observer(max_event_count=25, max_event_timestamps=ns, x_up_threshold=0.3, x_down_threshold=0.2, nhood_radius=0.1)
+    g = GpuRun(rt, model, stepper, observer, ns, bit_exact=True)
+    assert "-DCLODE_EXT_SMEM" in rt.program_source(g.prog)
+    g.setup(ts, x0, pars, sp, op, seed=3)
+    r = g.features()
+    lib = restate.OracleLib(Config(model, stepper, observer, ns, math="pm"))
+    o = run_oracle(lib, "features", ts, x0, pars, sp, op, seed=3)
+    assert_bit_equal(r, o, f"{model} {stepper} {observer} (extents in shared memory)")
+    g.sim.shift_x0()
+    g.sim.set_tspan(ts[1], ts[1] + (ts[1] - ts[0]))
+    r2 = g.features(initialize=0)
+    o2 = lib.features((ts[1], ts[1] + (ts[1] - ts[0])), o["xf"], pars, sp, op, o["dt"], o["rng"], initialize=False)
+    assert_bit_equal(r2, o2, "continued")
+    g.close()
