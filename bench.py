@@ -371,8 +371,10 @@ def run_ours(args):
     achieved_tf = w["flops_per_step"] * steps_per_pass * args.steps / (sum(kernel_ms) * 1e-3) / 1e12
     info = sim.kernel_info(_rt.KERNEL_TRAJECTORY if is_traj else _rt.KERNEL_FEATURES)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-    # (profiles/r01_*_summary.txt); None for workloads that were not captured
-    ncu_traffic = {"C2": 143.456768e6 + 122.234880e6, "C5": 21.757184e6 + 29.332668e9, "C5e": 18.968832e6 + 29.331877e9}
+    # (profiles/r01e_*_summary.txt; C3: the features kernel, the dominant launch of the pair — its writes are spill
+    # lines evicted from L2, not results); None for workloads that were not captured
+    ncu_traffic = {"C2": 141.124864e6 + 121.296640e6, "C3": 760.737280e6 + 2.706634e9,
+                   "C5": 21.410816e6 + 29.337310e9, "C5e": 20.577280e6 + 29.331946e9}
     traffic = ncu_traffic.get(args.workload) if n == default_n else None
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,

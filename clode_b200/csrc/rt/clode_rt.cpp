@@ -155,6 +155,12 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
     if (s.ext_smem) o.push_back("-DCLODE_EXT_SMEM");
+    if (const char *extra = std::getenv("CLODE_EXTRA_DEFINES")) { // development knob: space-separated -D options (A/B sweeps)
+        std::istringstream is(extra);
+        std::string tok;
+        while (is >> tok)
+            if (tok.rfind("-D", 0) == 0) o.push_back(tok);
+    }
     return o;
 }
 

@@ -78,3 +78,38 @@ def test_cuda_fast_exp_against_the_library_exp():
     ok = np.isfinite(lib) & (lib > np.finfo(np.float64).tiny)
     assert np.all(np.abs(fast[ok] - lib[ok]) <= 2 * np.spacing(lib[ok]))   # 0.52 + 1 ulp, in units of the larger spacing
     assert np.array_equal(fast[~ok], lib[~ok])                             # overflow / underflow: the library's own values
+
+
+DIV_RHS = """void getRHS(const realtype t, const realtype x_[], const realtype p_[], realtype dx_[], realtype aux_[], const realtype w_[]) {
+    dx_[0] = p_[0];
+    aux_[0] = div_norm(x_[0], p_[1]);   /* the engine's error-norm division (steppers.cuh), visible to the RHS text */
+    aux_[1] = div_nr(x_[0], p_[1]);     /* the bookkeeping division: two Newton steps */
+}
+"""
+
+
+@pytest.mark.gpu
+def test_cuda_engine_divisions_accuracy():
+    """production double: div_norm (one Newton step on the SFU reciprocal, used only inside the step-size controller's
+    error norm) is within 1e-11 of the IEEE quotient, div_nr (two steps, running means) within 2 ulp"""
+    n, rows = 4096, 60
+    prog = _rt.Program(DIV_RHS, "euler", 1, 2, 2, kernels=_rt.KERNEL_TRAJECTORY)
+    sim = _rt.Sim(prog)
+    sim.set_solver_params(dt=1.0, dtmax=1.0, abstol=1e-6, reltol=1e-3, max_steps=rows, max_store=rows + 1, nout=1)
+    sim.set_tspan(0.0, float(rows))
+    rng = np.random.default_rng(11)
+    x0 = rng.uniform(-5.0, 5.0, n)
+    pars = np.concatenate([rng.uniform(0.01, 3.0, n), 10.0 ** rng.uniform(-12, 12, n)])
+    sim.set_problem(x0, pars)
+    sim.seed_rng(1)
+    sim.trajectory()
+    tr = sim.get_trajectory()
+    keep = int(tr["n_stored"].min()) + 1
+    x = tr["x"].reshape(-1, n)[:keep]
+    aux = tr["aux"].reshape(-1, 2, n)[:keep]
+    sim.close()
+    want = x / pars[n:][None, :]
+    ok = want != 0.0
+    rel = np.abs(aux[:, 0][ok] - want[ok]) / np.abs(want[ok])
+    assert rel.max() < 1e-11, rel.max()
+    assert np.all(np.abs(aux[:, 1][ok] - want[ok]) <= 2 * np.spacing(np.abs(want[ok])))
