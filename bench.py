@@ -47,12 +47,13 @@ def workload(name: str, n_total: int, index):
     idx = np.asarray(index, dtype=np.int64)
     n = idx.size
     frac = idx.astype(np.float64) / max(n_total - 1, 1)
-    if name == "C2":
-        w = dict(model="lorenz63", stepper="dopri5", observer="basic", kind="features", tspan=(0.0, 100.0),
+    if name in ("C2", "C2l"):
+        # BASELINE.json configs[1] names both observers: C2 = basic (the headline), C2l = localmax (26 features)
+        w = dict(model="lorenz63", stepper="dopri5", observer="basic" if name == "C2" else "localmax", kind="features", tspan=(0.0, 100.0),
                  solver=dict(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, max_steps=10000000),
                  observer_params=dict(max_event_count=10000),
                  pars=np.concatenate([0.5 + 59.5 * frac, np.full(n, 10.0), np.full(n, 8.0 / 3.0)]),
-                 x0=np.ones(3 * n), desc="C2: Lorenz features, dopri5, observer basic, 2^20 parameter sets per GPU, f64")
+                 x0=np.ones(3 * n), desc=f"{name}: Lorenz features, dopri5, observer {'basic' if name == 'C2' else 'localmax'}, 2^20 parameter sets per GPU, f64")
     elif name == "C3":
         # 1024 x 1024 (gcal x gbk) grid, flattened row-major; bs23 + thresh2 (two-pass)
         side = int(round(n_total ** 0.5))

@@ -81,44 +81,6 @@ CLODE_DEV double abs_nn(const double v) { return __hiloint2double(__double2hiint
 CLODE_DEV double opaque(const double c) { double r; asm("mov.f64 %0, %1;" : "=d"(r) : "d"(c)); return r; }
 #endif
 
-// max(v, m) for v = |something| (non-negative, or NaN) and m >= 0, not NaN — the operands of the controller's error
-// norm.  For such values the order of the doubles is the order of their bit patterns as integers, so production
-// double compares on the integer pipe (2 ISETP for the 64-bit compare + 1 for "v is not NaN") instead of with a DSETP
-// on the FP64 pipe, which is the bottleneck of the step loop and issues compares at 70 % of its FMA rate
-// (profiles/r01_fp64_pipe_probe.log).  Same result as max_nn(v, m) for every input except NaN payloads whose upper
-// mantissa word is zero (treated as +Inf; CUDA arithmetic never produces them).
-#if CLODE_EXACT_ARITH || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_FLOAT_NORM_COMPARES)
-CLODE_DEV realtype max_abs_nn(const realtype v, const realtype m) { return max_nn(v, m); }
-CLODE_DEV bool gt_pos(const realtype a, const realtype b) { return a > b; }
-#else
-CLODE_DEV double max_abs_nn(const double v, const double m)
-{
-    const bool take = __double_as_longlong(v) > __double_as_longlong(m) && (unsigned int)__double2hiint(v) <= 0x7ff00000u;
-    return take ? v : m;
-}
-// a > b for a, b >= 0 and not NaN
-CLODE_DEV bool gt_pos(const double a, const double b) { return __double_as_longlong(a) > __double_as_longlong(b); }
-#endif
-
-// Step-size bookkeeping compares: h against the positive, finite bounds hmin / dtmax, and the remaining interval
-// against h.  A finite double of either sign compares with a POSITIVE one like their bit patterns do as signed
-// integers, so production double does these on the integer pipe as well.  (A NaN step — only possible when the
-// caller uploads NaN into the per-instance dt array — clamps to dtmax here and to hmin in the reference's fmax/fmin.)
-#if CLODE_EXACT_ARITH || defined(CLODE_SINGLE_PRECISION) || defined(CLODE_FLOAT_STEP_COMPARES)
-CLODE_DEV realtype clamp_step(const realtype h, const realtype lo, const realtype hi) { return clamp_nn(h, lo, hi); }
-CLODE_DEV realtype min_step(const realtype v, const realtype h) { return min_nn(v, h); }
-CLODE_DEV bool le_step(const realtype h, const realtype hmin) { return h <= hmin; }
-#else
-CLODE_DEV double clamp_step(const double h, const double lo, const double hi)
-{
-    const long long hb = __double_as_longlong(h);
-    const double up = hb > __double_as_longlong(lo) ? h : lo;
-    return __double_as_longlong(up) < __double_as_longlong(hi) ? up : hi;
-}
-CLODE_DEV double min_step(const double v, const double h) { return __double_as_longlong(v) < __double_as_longlong(h) ? v : h; }
-CLODE_DEV bool le_step(const double h, const double hmin) { return __double_as_longlong(h) <= __double_as_longlong(hmin); }
-#endif
-
 // a / b for the engine's own bookkeeping divisions (error normalisation, running means).
 // Reference-arithmetic builds: the IEEE division, as written in the reference.  Production double:
 // reciprocal by MUFU.RCP64H + two Newton steps, then one multiply — <= 2 ulp, no denormal / overflow
@@ -150,8 +112,12 @@ CLODE_DEV double div_nr(const double a, const double b)
 
 // err / scale of the step-size controller's error norm.  The quotient feeds a comparison with reltol and a clamped
 // fifth (third) root, so production double stops after ONE Newton step on the SFU seed (relative error < 1e-11,
-// measured on the GPU against the IEEE quotient, tests/test_fast_exp.py): 3 FP64-pipe instructions per variable instead of 5.
-#if CLODE_EXACT_ARITH || CLODE_FAST_SINGLE || defined(CLODE_TWO_STEP_NORM_DIVISION)
+// measured on the GPU against the IEEE quotient, tests/test_fast_exp.py): 3 FP64-pipe instructions per variable instead
+// of 5 (C2 58.99 -> 57.38 ms).  Moving the norm's and the step clamps' compares to the integer pipe (bit-pattern order of
+// non-negative doubles) was tried as well: 23 fewer FP64-pipe instructions but 27 more issue slots, and slower
+// (59.47 ms) — with the divisions trimmed the loop is issue-bound, not FP64-pipe-bound
+// (profiles/r01_integer_compares_and_norm_division_ab.log).
+#if CLODE_EXACT_ARITH || CLODE_FAST_SINGLE
 CLODE_DEV realtype div_norm(const realtype a, const realtype b) { return div_nr(a, b); }
 #else
 CLODE_DEV double div_norm(const double a, const double b)
@@ -175,11 +141,20 @@ struct Instance {
     RngStream rng;
 };
 
+// Noise of the next step, fixed_explicit_step.clh:29-33: w = randn / sqrt(dt).  dt is constant inside a kernel for the
+// (fixed-step) stochastic method, so production double divides ONCE per kernel (the compiler hoists the square root
+// but must keep the IEEE division in the loop) and multiplies by the reciprocal: the variate moves by at most one
+// ulp, the integer RNG stream not at all.
 CLODE_DEV void draw_noise(Instance &I)
 {
+#if CLODE_STOCHASTIC && !CLODE_EXACT_ARITH
+    const realtype scale = ONE / sqrt(I.dt);
+#endif
 #pragma unroll
     for (int j = 0; j < N_WIENER; ++j)
-#if CLODE_STOCHASTIC
+#if CLODE_STOCHASTIC && !CLODE_EXACT_ARITH
+        I.w[j] = rng_normal(I.rng) * scale;
+#elif CLODE_STOCHASTIC
         I.w[j] = rng_normal(I.rng) / sqrt(I.dt);
 #else
         I.w[j] = ZERO;
@@ -453,18 +428,18 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     const realtype hmin = step_floor(I.t, t_end, ctl.floor_hi_min);
     realtype t1, xn[NV], kn[NV], err[NV];
 
-    h = clamp_step(h, hmin, sp.dtmax);
+    h = clamp_nn(h, hmin, sp.dtmax);
     h = trial_step(I, h, t1, xn, kn, err);
 
     realtype nerr = opaque(ZERO);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         // fmax(fmax(|x|, |xn|), floor) and norm_inf's fmax(|e|, running), NaN operands ignored as in the reference
-        err[j] = div_norm(err[j], max_abs_nn(abs_nn(I.x[j]), max_abs_nn(abs_nn(xn[j]), floor_)));
-        nerr = max_abs_nn(abs_nn(err[j]), nerr);
+        err[j] = div_norm(err[j], max_nn(abs_nn(I.x[j]), max_nn(abs_nn(xn[j]), floor_)));
+        nerr = max_nn(abs_nn(err[j]), nerr);
     }
-    const bool reject = gt_pos(nerr, sp.reltol);
-    if (reject && le_step(h, hmin)) { // cannot shrink further: stepper() returns -1, state untouched
+    const bool reject = nerr > sp.reltol;
+    if (reject && h <= hmin) { // cannot shrink further: stepper() returns -1, state untouched
         I.dt = hmin;
         h = hmin;
         clean = true;
@@ -480,8 +455,8 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     }
     if (clean)
         h *= min_nn(factor, opaque(RCONST(5.0)));
-    h = min_step(t_end - t1, h); // fmin(h, t_end - t1): h is never NaN here
-    h = clamp_step(h, hmin, sp.dtmax);
+    h = min_nn(t_end - t1, h); // fmin(h, t_end - t1): h is never NaN here
+    h = clamp_nn(h, hmin, sp.dtmax);
     I.dt = h;
     I.t = t1;
 #pragma unroll
