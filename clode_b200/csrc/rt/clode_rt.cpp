@@ -229,6 +229,8 @@ struct PtxasShim {
     void (*release)(void *) = nullptr;
     bool load()
     {
+        if (const char *off = std::getenv("CLODE_NO_PTXAS_LIB")) // exercise the nvJitLink fallback (tests)
+            if (*off == '1') return false;
         const std::string path = own_dir() + "/libclode_ptxas.so";
         void *h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!h) return false;
