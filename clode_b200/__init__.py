@@ -15,7 +15,14 @@ _FRONT_END = ["CLDeviceType", "CLVendor", "DeviceInfo", "PlatformInfo", "OpenCLR
 _TEXT_FRONT_ENDS = {"OpenCLConverter": "function_converter", "OpenCLRhsEquation": "function_converter",
                     "convert_str_to_opencl": "function_converter", "convert_xpp_file": "xpp_parser",
                     "read_ode_parameters": "xpp_parser", "format_opencl_rhs": "xpp_parser"}
-__all__ = list(_FRONT_END) + list(_TEXT_FRONT_ENDS)
+# Python stand-ins of the OpenCL-C builtins, so that a right-hand side written as a Python function can call
+# `clode.exp`, `clode.heaviside`, `clode.pown`, ... and still run as plain Python (clode/__init__.py:13-67)
+_BUILTINS = ["acos", "acosh", "acospi", "asin", "asinh", "asinpi", "atan", "atan2", "atan2pi", "atanh", "atanpi", "cbrt",
+             "ceil", "copysign", "cos", "cosh", "cospi", "erf", "erfc", "exp", "exp10", "exp2", "expm1", "fabs", "fdim",
+             "floor", "fmod", "gamma", "heaviside", "hypot", "ilogb", "ldexp", "lgamma", "log", "log10", "log1p", "log2",
+             "nextafter", "pow", "pown", "powr", "remainder", "rint", "rootn", "rsqrt", "sin", "sinh", "sinpi", "sqrt",
+             "tan", "tanh", "tanpi", "trunc"]
+__all__ = list(_FRONT_END) + list(_TEXT_FRONT_ENDS) + _BUILTINS
 
 
 def __getattr__(name):
@@ -23,6 +30,9 @@ def __getattr__(name):
     if name in _TEXT_FRONT_ENDS:  # pure Python: Python / XPP -> OpenCL-C source (clode/__init__.py exports the same names)
         import importlib
         return getattr(importlib.import_module("." + _TEXT_FRONT_ENDS[name], __name__), name)
+    if name in _BUILTINS:
+        from . import opencl_builtins
+        return getattr(opencl_builtins, name)
     if name in _FRONT_END:
         from . import features, runtime, solver, trajectory
         from .cpp import clode_cpp_wrapper as w

@@ -37,6 +37,26 @@ def test_public_names_of_the_reference_package():
     assert [o.value for o in clode.Observer] == ["basic", "basicall", "localmax", "nhood1", "nhood2", "thresh2"]
 
 
+def test_every_name_the_reference_package_exports_exists_here():
+    """clode/__init__.py (imports + __all__) against this package, including the Python stand-ins of the OpenCL-C
+    builtins that Python right-hand sides call (clode.exp, clode.heaviside, clode.pown, ...)"""
+    import ast
+    import math
+
+    ref = os.path.join(os.environ.get("CLODE_REFERENCE", "/root/reference"), "clode", "__init__.py")
+    if os.path.exists(ref):
+        names = set()
+        for node in ast.walk(ast.parse(open(ref).read())):
+            if isinstance(node, ast.ImportFrom):
+                names |= {a.asname or a.name for a in node.names}
+        missing = sorted(n for n in names if not hasattr(clode, n))
+        assert not missing, missing
+    assert clode.exp(1.0) == math.e and clode.heaviside(-2.0) == 0.0 and clode.heaviside(3.0) == 1.0
+    assert clode.pown(2.0, 3) == 8.0 and clode.rootn(27.0, 3) == pytest.approx(3.0) and clode.sinpi(0.5) == pytest.approx(1.0)
+    from clode_b200 import cospi, exp10, rsqrt  # noqa: F401  (importable by name)
+    assert set(clode._BUILTINS) <= set(clode.__all__)
+
+
 def test_struct_defaults_match_the_reference_binding():
     sp = clode.SolverParams()  # clode/cpp/CLODEpython.cpp:229-235
     assert (sp.dt, sp.dtmax, sp.abstol, sp.reltol, sp.max_steps, sp.max_store, sp.nout) == (0.1, 0.5, 1e-6, 1e-3, 1000000, 1000000, 1)
