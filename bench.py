@@ -210,7 +210,7 @@ def run_ours(args):
                        work_queue=bool(args.work_queue), block_size=args.block, min_blocks_per_sm=args.min_blocks,
                        staged_trajectory=bool(args.staged), observer_in_shared=bool(args.obs_smem),
                        single_precision=bool(args.single), ieee_constant_division=bool(args.ieee_div),
-                       library_exp=bool(args.library_exp))
+                       library_exp=bool(args.library_exp), bit_exact=bool(args.bit_exact))
     sim = _rt.Sim(prog, device=local)
     sim.set_solver_params(**w["solver"])
     sim.set_observer_params(**w["observer_params"])
@@ -440,6 +440,7 @@ def main():
     ap.add_argument("--single", type=int, default=0, help="single precision (the reference's Python default); not the headline")
     ap.add_argument("--ieee-div", type=int, default=0, help="leave `x / literal` to ptxas' generic division (A/B of the PTX pass)")
     ap.add_argument("--library-exp", type=int, default=0, help="CUDA's exp instead of device/fast_exp.cuh (A/B)")
+    ap.add_argument("--bit-exact", type=int, default=0, help="bit-exact tier (no FMA contraction, portable math): the tier with identical step counts")
     ap.add_argument("--shuffle", type=int, default=0, help="randomly permute the parameter grid (heterogeneous warps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -486,23 +486,41 @@ struct clode_sim {
         b.ptr = 0; b.bytes = 0;
     }
 
+    // Host <-> device transfers are issued on the simulation's own stream and completed before the call returns:
+    // the stream is CU_STREAM_NON_BLOCKING, so a copy on the legacy NULL stream would not be ordered against the
+    // kernels launched on it (a pageable cuMemcpyHtoD may return once the bytes are staged, before the DMA lands).
+    int h2d(CUdeviceptr dst, const void *src, size_t bytes, const char *what)
+    {
+        if (bytes == 0) return CLODE_OK;
+        int rc = cu(d->cuMemcpyHtoDAsync(dst, src, bytes, stream), what);
+        if (rc) return rc;
+        return cu(d->cuStreamSynchronize(stream), what);
+    }
+    int d2h(void *dst, CUdeviceptr src, size_t bytes, const char *what)
+    {
+        if (bytes == 0) return CLODE_OK;
+        int rc = cu(d->cuMemcpyDtoHAsync(dst, src, bytes, stream), what);
+        if (rc) return rc;
+        return cu(d->cuStreamSynchronize(stream), what);
+    }
+
     // host double[] -> device realtype[]
     int upload_real(Buffer &b, const double *src, size_t count, const char *what)
     {
         if (count * real_size != b.bytes) return fail(CLODE_ERR_INVALID, std::string(what) + ": size mismatch");
         if (count == 0) return CLODE_OK;
-        if (real_size == 8) return cu(d->cuMemcpyHtoD(b.ptr, src, count * 8), what);
+        if (real_size == 8) return h2d(b.ptr, src, count * 8, what);
         std::vector<float> tmp(count);
         for (size_t k = 0; k < count; ++k) tmp[k] = (float)src[k];
-        return cu(d->cuMemcpyHtoD(b.ptr, tmp.data(), count * 4), what);
+        return h2d(b.ptr, tmp.data(), count * 4, what);
     }
     int download_real(const Buffer &b, double *dst, size_t count, const char *what)
     {
         if (count * real_size > b.bytes) return fail(CLODE_ERR_INVALID, std::string(what) + ": size mismatch");
         if (count == 0) return CLODE_OK;
-        if (real_size == 8) return cu(d->cuMemcpyDtoH(dst, b.ptr, count * 8), what);
+        if (real_size == 8) return d2h(dst, b.ptr, count * 8, what);
         std::vector<float> tmp(count);
-        int rc = cu(d->cuMemcpyDtoH(tmp.data(), b.ptr, count * 4), what);
+        int rc = d2h(tmp.data(), b.ptr, count * 4, what);
         if (rc) return rc;
         for (size_t k = 0; k < count; ++k) dst[k] = (double)tmp[k];
         return CLODE_OK;
@@ -1085,8 +1103,9 @@ int clode_sim_seed_rng(clode_sim *s, int64_t seed, uint64_t offset, uint64_t n_g
     if (n_global == 0) n_global = s->n;
     std::vector<uint64_t> st(2 * s->n);
     for (size_t i = 0; i < s->n; ++i) {
-        st[i] = (uint64_t)(seed + (int64_t)(offset + i));
-        st[s->n + i] = (uint64_t)(seed + (int64_t)(n_global + offset + i));
+        // `RNGstate[i] = mySeed + i` with cl_int operands (CLODE.cpp:450-453): 32-bit wrap-around, then sign extension
+        st[i] = (uint64_t)(int64_t)(int32_t)((uint32_t)seed + (uint32_t)(offset + i));
+        st[s->n + i] = (uint64_t)(int64_t)(int32_t)((uint32_t)seed + (uint32_t)(n_global + offset + i));
     }
     return clode_sim_set_rng_state(s, st.data(), st.size());
 }
@@ -1096,7 +1115,7 @@ int clode_sim_set_rng_state(clode_sim *s, const uint64_t *state, size_t count)
     if (!s || !state) return fail(CLODE_ERR_INVALID, "null argument");
     if (count != 2 * s->n) return fail(CLODE_ERR_INVALID, "set_rng_state: expected 2*nPts words");
     clode_sim::Scope scope(s);
-    return s->cu(s->d->cuMemcpyHtoD(s->rng.ptr, state, 8 * count), "set_rng_state");
+    return s->h2d(s->rng.ptr, state, 8 * count, "set_rng_state");
 }
 
 int clode_sim_get_rng_state(clode_sim *s, uint64_t *state, size_t count)
@@ -1104,7 +1123,7 @@ int clode_sim_get_rng_state(clode_sim *s, uint64_t *state, size_t count)
     if (!s || !state) return fail(CLODE_ERR_INVALID, "null argument");
     if (count != 2 * s->n) return fail(CLODE_ERR_INVALID, "get_rng_state: expected 2*nPts words");
     clode_sim::Scope scope(s);
-    return s->cu(s->d->cuMemcpyDtoH(state, s->rng.ptr, 8 * count), "get_rng_state");
+    return s->d2h(state, s->rng.ptr, 8 * count, "get_rng_state");
 }
 
 static int run_transient(clode_sim *s, bool blocking)
@@ -1261,8 +1280,17 @@ int clode_sim_trajectory_stream(clode_sim *s, size_t chunk_rows, double *t, doub
     if (!s->flags_host && (rc = s->cu(s->d->cuMemHostAlloc((void **)&s->flags_host, 8, 0), "cuMemHostAlloc"))) return rc;
 
     const HostOut out = {t, x, dx, aux};
-    std::future<int> copied[2];
-    auto drain = [&](int b) { return copied[b].valid() ? copied[b].get() : (int)CLODE_OK; };
+    // the copies run on helper threads, whose thread-local error text the caller cannot see: it travels with the status
+    std::future<std::pair<int, std::string>> copied[2];
+    auto copy_out = [](clode_sim *sim, int b, size_t row0, size_t rows, HostOut o) {
+        const int rc = copy_chunk_out(sim, b, row0, rows, o);
+        return std::make_pair(rc, rc ? g_error : std::string());
+    };
+    auto drain = [&](int b) {
+        if (!copied[b].valid()) return (int)CLODE_OK;
+        const std::pair<int, std::string> r = copied[b].get();
+        return r.first ? fail(r.first, r.second) : (int)CLODE_OK;
+    };
     float kernel_ms = 0.f;
     rc = CLODE_OK;
     for (size_t k = 0; k * R < total_rows; ++k) {
@@ -1287,14 +1315,16 @@ int clode_sim_trajectory_stream(clode_sim *s, size_t chunk_rows, double *t, doub
         // rows actually written by this launch, clipped to the max_store rows the API returns
         const size_t stop = std::min<size_t>({(size_t)s->flags_host[1] + 1, row_end, (size_t)s->sp.max_store});
         if (stop > row_begin)
-            copied[b] = std::async(std::launch::async, copy_chunk_out, s, b, row_begin, stop - row_begin, out);
+            copied[b] = std::async(std::launch::async, copy_out, s, b, row_begin, stop - row_begin, out);
         if (!any_live) break;
     }
+    const std::string first_error = rc ? g_error : std::string();
     const int rc0 = drain(0), rc1 = drain(1);
-    if (!rc) rc = rc0 ? rc0 : rc1;
+    if (rc) g_error = first_error; // the launch-side failure came first; keep its text
+    else rc = rc0 ? rc0 : rc1;
     s->last_ms = kernel_ms;
     if (rc) return rc;
-    if (n_stored) return s->cu(s->d->cuMemcpyDtoH(n_stored, s->n_stored.ptr, 4 * n), "trajectory_stream: nStored");
+    if (n_stored) return s->d2h(n_stored, s->n_stored.ptr, 4 * n, "trajectory_stream: nStored");
     return CLODE_OK;
 }
 
@@ -1393,7 +1423,7 @@ int clode_sim_get_n_stored(clode_sim *s, int *out, size_t count)
     if (!s || !out) return fail(CLODE_ERR_INVALID, "null argument");
     if (count != s->n || !s->n_stored.ptr) return fail(CLODE_ERR_STATE, "get_n_stored: run trajectory() first / wrong count");
     clode_sim::Scope scope(s);
-    return s->cu(s->d->cuMemcpyDtoH(out, s->n_stored.ptr, 4 * count), "get_n_stored");
+    return s->d2h(out, s->n_stored.ptr, 4 * count, "get_n_stored");
 }
 
 int clode_sim_get_steps(clode_sim *s, uint32_t *out, size_t count)
@@ -1401,7 +1431,7 @@ int clode_sim_get_steps(clode_sim *s, uint32_t *out, size_t count)
     if (!s || !out) return fail(CLODE_ERR_INVALID, "null argument");
     if (count != s->n || !s->steps.ptr) return fail(CLODE_ERR_STATE, "get_steps: wrong count");
     clode_sim::Scope scope(s);
-    return s->cu(s->d->cuMemcpyDtoH(out, s->steps.ptr, 4 * count), "get_steps");
+    return s->d2h(out, s->steps.ptr, 4 * count, "get_steps");
 }
 
 int clode_sim_n_features(clode_sim *s, int *n_features)

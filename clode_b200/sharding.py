@@ -3,7 +3,11 @@ variable-major ensemble arrays, and the single exchange step — the final gathe
 matrices to rank 0 (NCCL over NVLink on GPU tensors, gloo on CPU tensors in the tests).
 
 Instances are independent, so nothing else is communicated.  The in-process
-multi-GPU path of the C++ classes (CLODE::setNpts) uses the same contiguous, warp-aligned ranges.
+multi-GPU path of the C++ classes (CLODE::setNpts) uses the INTERLEAVED assignment (`interleaved` below: shard g
+owns instances g, g+G, ...); `partition` (contiguous ranges) is kept for callers that need contiguous slices.
+
+Seeding follows CLODE::seedRNG(cl_int) (clode/cpp/CLODE.cpp:447-453) literally: the word index is added to the seed
+in 32-bit signed arithmetic (`mySeed + (cl_int)i` wraps) and the sum is sign-extended to 64 bits — `_seed_words`.
 """
 from __future__ import annotations
 
@@ -33,10 +37,16 @@ def take_rows(flat: np.ndarray, rows: int, n_total: int, index: np.ndarray) -> n
     return np.ascontiguousarray(np.asarray(flat).reshape(rows, n_total)[:, index]).ravel()
 
 
+def _seed_words(seed: int, k: np.ndarray) -> np.ndarray:
+    """RNGstate[k] = (cl_ulong)(mySeed + (cl_int)k): int32 wrap-around, then sign extension"""
+    s = (np.int64(seed) + np.asarray(k, dtype=np.int64)).astype(np.int32)  # wraps modulo 2^32
+    return s.astype(np.int64).astype(np.uint64)
+
+
 def seed_states_for(seed: int, n_total: int, index: np.ndarray) -> np.ndarray:
     """global seeding rule (clode/cpp/CLODE.cpp:447-453) for an arbitrary instance index set"""
     i = np.asarray(index, dtype=np.int64)
-    return np.concatenate([(np.int64(seed) + i).astype(np.uint64), (np.int64(seed) + np.int64(n_total) + i).astype(np.uint64)])
+    return np.concatenate([_seed_words(seed, i), _seed_words(seed, np.int64(n_total) + i)])
 
 
 def gather_interleaved(local, rows: int, n_total: int, dst: int = 0):
@@ -70,8 +80,7 @@ def shard_rows(flat: np.ndarray, rows: int, n_total: int, lo: int, hi: int) -> n
 def seed_states(seed: int, n_total: int, lo: int, hi: int) -> np.ndarray:
     """RNG state words of instances [lo, hi) under the reference's global rule RNGstate[k] = seed + k
     (clode/cpp/CLODE.cpp:447-453): instance i owns words i and n_total + i"""
-    i = np.arange(lo, hi, dtype=np.int64)
-    return np.concatenate([(np.int64(seed) + i).astype(np.uint64), (np.int64(seed) + np.int64(n_total) + i).astype(np.uint64)])
+    return seed_states_for(seed, n_total, np.arange(lo, hi, dtype=np.int64))
 
 
 def gather_rows(local, rows: int, n_total: int, dst: int = 0):

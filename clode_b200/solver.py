@@ -38,6 +38,7 @@ def _as_f(a: np.ndarray) -> np.ndarray:
 class Simulator:
     _integrator: SimulatorBase
     _runtime: OpenCLResource
+    _generated_files: set = set()  # temporary getRHS files written for Python right-hand sides
 
     def __init__(
         self,
@@ -80,6 +81,13 @@ class Simulator:
 
         self._create_integrator()
         self._build_cl_program()
+        if src_file in Simulator._generated_files:  # the C++ layer holds the source text now (CLODE::setProblemInfo)
+            import os
+            Simulator._generated_files.discard(src_file)
+            try:
+                os.remove(src_file)
+            except OSError:
+                pass
 
         self._sp = solver_parameters if solver_parameters is not None else SolverParams(
             dt, dtmax, abstol, reltol, max_steps, max_store, nout)
@@ -114,6 +122,11 @@ class Simulator:
         fd, path = tempfile.mkstemp(prefix="clode_rhs_", suffix=".cl")
         with os.fdopen(fd, "w") as f:
             f.write(text)
+        # ProblemInfo / setProblemInfo read the file when the integrator is created; removed at interpreter exit at the
+        # latest (and by the simulator's finalizer, see __init__)
+        import atexit
+        atexit.register(lambda p=path: os.path.exists(p) and os.remove(p))
+        Simulator._generated_files.add(path)
         return path
 
     # ---- properties (clode/solver.py:83-119) ---------------------------------------------------

@@ -225,6 +225,6 @@ def seed_states(seed: int, n_pts: int, offset: int = 0, n_global: int | None = N
     ensemble must use to reproduce the unsharded stream."""
     n_global = n_pts if n_global is None else n_global
     i = np.arange(offset, offset + n_pts, dtype=np.int64)
-    s0 = (np.int64(seed) + i).astype(np.uint64)
-    s1 = (np.int64(seed) + np.int64(n_global) + i).astype(np.uint64)
-    return np.concatenate([s0, s1])
+    # `mySeed + i` is evaluated in cl_int (32-bit, wraps) and then widened to cl_ulong (sign extension)
+    wrap = lambda k: (np.int64(seed) + k).astype(np.int32).astype(np.int64).astype(np.uint64)
+    return np.concatenate([wrap(i), wrap(np.int64(n_global) + i)])
