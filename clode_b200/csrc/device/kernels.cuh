@@ -83,6 +83,20 @@ struct KernelArgs {
     unsigned int block_order;
     const unsigned long long *cost_in; // [2] or null
     unsigned long long *cost_out;      // [2] or null
+    // Cost-sorted, chunked execution of the adaptive time loops (run_ensemble, "Scheduling" below).  A launch covers
+    // `n_slots` thread slots; slot s integrates instance perm[s] (identity when perm is null) for at most
+    // `attempt_budget` attempts and then either finishes it (end) or PARKS it — the complete loop-carried state goes
+    // to park_real / park_uint (+ the observer record) — so that a later launch (`sched_resume`) continues it
+    // bit-identically on whatever lane the scheduler assigns.
+    const unsigned int *perm;      // [n_slots] or null
+    unsigned long long n_slots;    // 0 = n
+    unsigned int attempt_budget;   // 0xffffffff: run to completion
+    unsigned int sched_resume;     // 1: continue parked instances
+    void *park_real;               // [2 N_VAR + NA_ + 3][n]: x, k1, aux, t, dt, trial step h
+    unsigned int *park_uint;       // [2][n]: accepted steps so far; flags (bit 0 `clean`, bit 1 finished)
+    // written by clode_sched_scan on the device, so that a whole schedule is enqueued without a host round trip:
+    // [0] live instances (= slots of the next launch), [1] dearest non-empty bucket, [2] attempt budget of the next launch
+    const unsigned int *sched_state; // or null: n_slots / attempt_budget above apply
 };
 
 extern "C" __constant__ KernelArgs clode_args;
@@ -150,6 +164,80 @@ CLODE_DEV void store_instance(const Instance &I, const KernelArgs &a, const size
     if (a.steps) a.steps[i] = steps;
 }
 
+// ---- parked state of an instance between two launches of a chunked time loop ---------------------------------------
+// Everything the attempt loop carries: x, the FSAL slope k1 (stored, not recomputed: a recomputed slope is a different
+// inlined copy of getRHS and may contract differently), aux, t, dt, the trial step h, the accepted-step counter and the
+// controller's `clean` flag.  Parameters are re-read from pars; the RNG state is not touched by adaptive steppers
+// (only they are scheduled) and stays where it is.
+#define PARK_X 0
+#define PARK_K1 (NV)
+#define PARK_AUX (2 * NV)
+#define PARK_T (2 * NV + NA_)
+#define PARK_DT (2 * NV + NA_ + 1)
+#define PARK_H (2 * NV + NA_ + 2)
+#define PARK_ROWS (2 * NV + NA_ + 3)
+#define PARK_FLAG_CLEAN 1u
+#define PARK_FLAG_FINISHED 2u
+
+CLODE_DEV void park_instance(const Instance &I, const KernelArgs &a, const size_t i, const unsigned int step,
+                             const realtype h, const bool clean)
+{
+    const size_t n = a.n;
+    realtype *pr = (realtype *)a.park_real + i;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        pr[(size_t)(PARK_X + j) * n] = I.x[j];
+        pr[(size_t)(PARK_K1 + j) * n] = I.k1[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NA_; ++j)
+        pr[(size_t)(PARK_AUX + j) * n] = I.aux[j];
+    pr[(size_t)PARK_T * n] = I.t;
+    pr[(size_t)PARK_DT * n] = I.dt;
+    pr[(size_t)PARK_H * n] = h;
+    a.park_uint[i] = step;
+    a.park_uint[n + i] = clean ? PARK_FLAG_CLEAN : 0u;
+}
+
+CLODE_DEV void unpark_instance(Instance &I, const KernelArgs &a, const size_t i, unsigned int &step, realtype &h, bool &clean)
+{
+    const size_t n = a.n;
+    const realtype *pr = (const realtype *)a.park_real + i, *pars = (const realtype *)a.pars;
+#pragma unroll
+    for (int j = 0; j < N_PAR; ++j)
+        I.p[j] = __ldg(pars + (size_t)j * n + i);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        I.x[j] = pr[(size_t)(PARK_X + j) * n];
+        I.k1[j] = pr[(size_t)(PARK_K1 + j) * n];
+    }
+#pragma unroll
+    for (int j = 0; j < NA_; ++j)
+        I.aux[j] = pr[(size_t)(PARK_AUX + j) * n];
+    I.t = pr[(size_t)PARK_T * n];
+    I.dt = pr[(size_t)PARK_DT * n];
+    h = pr[(size_t)PARK_H * n];
+    I.rng.s0 = a.rng[i];
+    I.rng.s1 = a.rng[n + i];
+    I.rng.have_spare = false;
+    I.rng.spare = ZERO;
+#pragma unroll
+    for (int j = 0; j < NW_; ++j)
+        I.w[j] = ZERO;
+    step = a.park_uint[i];
+    clean = (a.park_uint[n + i] & PARK_FLAG_CLEAN) != 0u;
+}
+
+// an instance finished inside a scheduled launch: the scheduler drops it, and its accepted-step count is the cost
+// estimate for a later pass over the same trajectory (warm-up -> features of the two-pass observers)
+CLODE_DEV void mark_finished(const KernelArgs &a, const size_t i, const unsigned int step)
+{
+    if (a.park_uint) {
+        a.park_uint[i] = step;
+        a.park_uint[a.n + i] = PARK_FLAG_FINISHED;
+    }
+}
+
 // advance by one ATTEMPT; true when an accepted (or abandoned, flag -1) step completed
 #if !CLODE_ADAPTIVE
 struct Controller {};
@@ -196,12 +284,26 @@ template <class Job> CLODE_DEV void run_ensemble(const KernelArgs &a, Job &job)
     }
 #endif
     const size_t chunk = reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
-    const size_t i = chunk * (size_t)blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    job.begin(i);
-    while (job.live())
+    const size_t slot = chunk * (size_t)blockDim.x + threadIdx.x;
+    const size_t n_slots = a.sched_state ? (size_t)a.sched_state[0] : (a.n_slots ? (size_t)a.n_slots : (size_t)a.n);
+    if (slot >= n_slots) return;
+    // Scheduling: the host sorts the unfinished instances by predicted remaining cost (clode_sched_* below) so that
+    // the lanes of a warp, and the warps of a block, hold instances of similar cost and the dearest start first
+    const size_t i = a.perm ? (size_t)a.perm[slot] : slot;
+    if (a.sched_resume) job.resume(i);
+    else job.begin(i);
+    // the budget of a sorted round comes from the scan kernel unless the host asks for a run to completion
+    unsigned int left = (a.sched_state && a.attempt_budget != 0xffffffffu) ? a.sched_state[2] : a.attempt_budget;
+    while (job.live() && left != 0u) {
         job.attempt();
+        --left;
+    }
+    if (job.live()) {
+        job.park(i);
+        return;
+    }
     job.end(i);
+    mark_finished(a, i, job.step);
 #ifndef __CUDACC_EMU__
     if (a.cost_out) { // one atomic per warp and half
         const unsigned int mask = __activemask();
@@ -263,6 +365,8 @@ struct TransientJob {
     __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps; }
     __device__ __forceinline__ void attempt() { if (advance(I, h, clean, sp, ctl, t_end)) ++step; }
     __device__ __forceinline__ void end(size_t i) { store_instance(I, a, i, step); }
+    __device__ __forceinline__ void park(size_t i) { park_instance(I, a, i, step, h, clean); }
+    __device__ __forceinline__ void resume(size_t i) { unpark_instance(I, a, i, step, h, clean); }
 };
 
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_TRANSIENT)
@@ -272,6 +376,134 @@ clode_transient()
     TransientJob job(clode_args);
     run_ensemble(clode_args, job);
 }
+
+// ---- Scheduling: cost-sorted instance order for the adaptive time loops ------------------------------------------
+// Adaptive instances of one ensemble differ in cost by an order of magnitude (Lorenz r-sweep: 300 .. 6500 attempts;
+// a bursting-model grid mixes silent, spiking and bursting cells).  A warp runs as long as its dearest lane and a launch
+// as long as its last block, so WHICH instances share a warp and WHEN the dear ones start decide the lane and SM
+// utilisation — on an unsorted parameter set half the lanes idle (C2 shuffled: 122 ms against 70 ms sorted).
+// The runtime therefore runs every adaptive time loop as a short PILOT launch in the caller's order (a fixed
+// attempt budget, nobody finishes, no divergence), then sorts the unfinished instances by predicted remaining cost,
+//     remaining = accepted steps so far * (t_end - t) / (t - t0)        (average cost per unit of time so far),
+// longest first, and continues them in launches of bounded attempt budget, re-sorting in between: lanes of a warp hold
+// instances of equal predicted cost, the dearest blocks start first (longest-processing-time-first), a misprediction
+// costs at most one budget, and the tail of a launch is short because its last blocks are its cheapest.  For the
+// features pass of a two-pass observer the warm-up pass has just integrated the same trajectories, so its step counts
+// are the exact costs (`by_steps`).  Results do not depend on the order: every instance's arithmetic is its own.
+//
+// The sort is a one-pass counting sort on a logarithmic key: bucket = the top 5 mantissa bits and the exponent of the
+// cost as a float (2 % resolution, 1024 buckets, dearest first): histogram (shared-memory privatised), scan (one
+// block), scatter (block-aggregated cursors).  Order inside a bucket is arbitrary.
+#ifndef __CUDACC_EMU__
+#define SCHED_BUCKETS 1024
+#define SCHED_BLOCK 256
+
+CLODE_DEV unsigned int sched_bucket_of(const float cost)
+{
+    // cost in [1, 2^31): biased exponent 127..157; NaN / Inf / huge -> dearest bucket, < 1 -> cheapest
+    const int q = (int)(__float_as_uint(cost) >> 18) - (127 << 5);
+    const int b = cost != cost ? SCHED_BUCKETS - 1 : (q < 0 ? 0 : (q > SCHED_BUCKETS - 1 ? SCHED_BUCKETS - 1 : q));
+    return (unsigned int)(SCHED_BUCKETS - 1 - b); // bucket 0 = dearest
+}
+
+// pass 1: bucket of every live slot (0xffffffff: finished, dropped) + global histogram
+extern "C" __global__ void __launch_bounds__(SCHED_BLOCK)
+clode_sched_histogram(const unsigned int *perm_in, const unsigned int *slots_dev, const unsigned long long n,
+                      const void *park_real, const unsigned int *park_uint, const double t0, const double t1,
+                      const unsigned int by_steps, unsigned int *bucket, unsigned int *hist)
+{
+    const size_t n_slots = slots_dev ? (size_t)slots_dev[0] : (size_t)n; // slots of the order being re-sorted
+    __shared__ unsigned int h[SCHED_BUCKETS];
+    for (int k = threadIdx.x; k < SCHED_BUCKETS; k += SCHED_BLOCK) h[k] = 0u;
+    __syncthreads();
+    const size_t slot = blockIdx.x * (size_t)SCHED_BLOCK + threadIdx.x;
+    if (slot < n_slots) {
+        const size_t i = perm_in ? (size_t)perm_in[slot] : slot;
+        unsigned int b = 0xffffffffu;
+        const unsigned int steps = park_uint[i];
+        if (by_steps) {
+            b = sched_bucket_of((float)steps);
+        } else if (!(park_uint[n + i] & PARK_FLAG_FINISHED)) {
+            const realtype t = ((const realtype *)park_real)[(size_t)PARK_T * n + i];
+            const float done = (float)((double)t - t0), left = (float)(t1 - (double)t);
+            b = sched_bucket_of(done > 0.0f ? (float)steps * (left / done) : 3.0e38f);
+        }
+        bucket[slot] = b;
+        if (b != 0xffffffffu) atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SCHED_BUCKETS; k += SCHED_BLOCK)
+        if (h[k]) atomicAdd(&hist[k], h[k]);
+}
+
+// pass 2 (one block): exclusive scan of the histogram -> bucket cursors; result = {live instances, dearest non-empty
+// bucket, attempt budget of the next launch} (KernelArgs::sched_state)
+extern "C" __global__ void __launch_bounds__(SCHED_BUCKETS)
+clode_sched_scan(const unsigned int *hist, unsigned int *cursor, unsigned int *result, const float budget_fraction,
+                 const unsigned int budget_min)
+{
+    __shared__ unsigned int warp_sum[SCHED_BUCKETS / 32];
+    __shared__ unsigned int first;
+    const unsigned int k = threadIdx.x, lane = k & 31u, w = k >> 5;
+    if (k == 0) first = SCHED_BUCKETS;
+    const unsigned int v = hist[k];
+    unsigned int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned int)d) incl += up;
+    }
+    if (lane == 31u) warp_sum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= (unsigned int)d) s += up;
+        }
+        warp_sum[lane] = s; // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned int before = (w ? warp_sum[w - 1] : 0u) + incl - v;
+    cursor[k] = before;
+    if (v) atomicMin(&first, k);
+    __syncthreads();
+    if (k == SCHED_BUCKETS - 1) {
+        result[0] = before + v;
+        result[1] = first;
+        // attempt budget of the next launch: a fraction of the dearest live instance's predicted remaining cost
+        // (upper edge of its bucket), so that mispredictions are re-sorted after at most that many attempts
+        const unsigned int q = (unsigned int)(SCHED_BUCKETS - first) + (127u << 5); // bucket `first` spans [2^.., next edge)
+        const float top = first < SCHED_BUCKETS ? __uint_as_float(q << 18) : 0.0f;
+        const float want = fminf(top * budget_fraction, 1.0e9f);
+        result[2] = max(budget_min, (unsigned int)want);
+    }
+}
+
+// pass 3: instance indices into their bucket ranges
+extern "C" __global__ void __launch_bounds__(SCHED_BLOCK)
+clode_sched_scatter(const unsigned int *perm_in, const unsigned int *slots_dev, const unsigned long long n,
+                    const unsigned int *bucket, unsigned int *cursor, unsigned int *perm_out)
+{
+    const size_t n_slots = slots_dev ? (size_t)slots_dev[0] : (size_t)n;
+    __shared__ unsigned int h[SCHED_BUCKETS];
+    for (int k = threadIdx.x; k < SCHED_BUCKETS; k += SCHED_BLOCK) h[k] = 0u;
+    __syncthreads();
+    const size_t slot = blockIdx.x * (size_t)SCHED_BLOCK + threadIdx.x;
+    unsigned int b = 0xffffffffu, rank = 0u, inst = 0u;
+    if (slot < n_slots) {
+        b = bucket[slot];
+        inst = perm_in ? perm_in[slot] : (unsigned int)slot;
+        if (b != 0xffffffffu) rank = atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SCHED_BUCKETS; k += SCHED_BLOCK)
+        if (h[k]) h[k] = atomicAdd(&cursor[k], h[k]); // count -> base of this block's range in bucket k
+    __syncthreads();
+    if (b != 0xffffffffu) perm_out[h[b] + rank] = inst;
+}
+#endif // !__CUDACC_EMU__
 
 #ifdef CLODE_WITH_FEATURES
 // Where the observer state lives while an instance is being integrated.
@@ -354,6 +586,24 @@ struct WarmupJob {
         ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
         ob.visit(st);
     }
+    // A parked warm-up carries only what the warm-up accumulates (visit_warmup: a few extents), in the first rows of
+    // the observer record, which end() overwrites with the complete record anyway.  Everything else in the observer is
+    // what init() derives from the initial state, so resume() re-derives it from x0 exactly as begin() does — loading
+    // the whole record instead would keep 60-90 reals alive through the warm-up loop (+600 B of spills for thresh2).
+    __device__ __forceinline__ void park(size_t i)
+    {
+        park_instance(I, a, i, step, h, clean);
+        ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit_warmup(st);
+    }
+    __device__ __forceinline__ void resume(size_t i)
+    {
+        load_instance(I, a, i);
+        ob.init(I);
+        unpark_instance(I, a, i, step, h, clean);
+        ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit_warmup(ld);
+    }
 };
 
 extern "C" __global__ void __launch_bounds__(CLODE_BLOCK, CLODE_MIN_BLOCKS_INIT)
@@ -419,6 +669,20 @@ struct FeaturesJob {
         ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
         ob.visit(st);
         store_instance(I, a, i, step);
+    }
+    // parked as it is in the loop: the time-weighted means stay in their in-kernel (integral) form, no re-basing
+    __device__ __forceinline__ void park(size_t i)
+    {
+        park_instance(I, a, i, step, h, clean);
+        ObsStore st = {(realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit(st);
+    }
+    __device__ __forceinline__ void resume(size_t i)
+    {
+        unpark_instance(I, a, i, step, h, clean);
+        ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
+        ob.visit(ld);
+        alive = true; // it was parked because it was
     }
 };
 
@@ -559,6 +823,10 @@ struct TrajectoryJob {
         store_instance(I, a, i, step);
         if (a.rs_uint) suspend_instance(I, a, i, step, row, unfinished());
     }
+    // trajectories are chunked by stored rows (suspend_instance / resume_instance), not by the attempt scheduler:
+    // a permuted instance order would turn the coalesced row stores into scattered ones
+    __device__ __forceinline__ void park(size_t i) { end(i); }
+    __device__ __forceinline__ void resume(size_t i) { begin(i); }
 };
 
 #if defined(CLODE_TRAJ_STAGED) && !CLODE_ADAPTIVE && !defined(CLODE_WORK_QUEUE)

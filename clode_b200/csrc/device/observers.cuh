@@ -78,6 +78,19 @@ CLODE_DEV void mean_count(realtype *mean, realtype v, unsigned int count)
     if (count == 1) *mean = v;
     else if (count > 1) *mean += div_nr(v - *mean, (realtype)count);
 }
+// A mean over EVERY accepted step (the step-size statistic of the event observers, nhood1's per-step means): with
+// count = 1, 2, 3, ... the recurrence above is the plain average, so the production build carries the SUM while a
+// kernel runs — one addition per step instead of an int-to-double conversion and a division on a dependent chain — and
+// converts on entry / exit like the time-weighted means (open_steps / close_steps).
+#if CLODE_INTEGRAL_MEANS
+CLODE_DEV void mean_steps(realtype *acc, realtype v, unsigned int) { *acc += v; }
+CLODE_DEV realtype open_steps(realtype mean, unsigned int count) { return mean * (realtype)count; }
+CLODE_DEV realtype close_steps(realtype sum, unsigned int count) { return count > 0 ? sum / (realtype)count : sum; }
+#else
+CLODE_DEV void mean_steps(realtype *acc, realtype v, unsigned int count) { mean_count(acc, v, count); }
+CLODE_DEV realtype open_steps(realtype mean, unsigned int) { return mean; }
+CLODE_DEV realtype close_steps(realtype mean, unsigned int) { return mean; }
+#endif
 
 // (max, min, running mean) accumulator used for every per-event statistic
 struct Tri {
@@ -88,6 +101,13 @@ struct Tri {
         hi = max_nn(v, hi);
         lo = min_nn(v, lo);
         mean_count(&mean, v, count);
+    }
+    // the same for a statistic pushed on every accepted step (see mean_steps)
+    __device__ __forceinline__ void push_step(realtype v, unsigned int count)
+    {
+        hi = max_nn(v, hi);
+        lo = min_nn(v, lo);
+        mean_steps(&mean, v, count);
     }
     template <class V> __device__ __forceinline__ void visit(V &v) { v(hi); v(lo); v(mean); }
 };
@@ -189,6 +209,20 @@ struct Extents {
         }
 #endif
     }
+    __device__ __forceinline__ void open_counts(unsigned int count)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xmean[j] = open_steps(xmean[j], count);
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) amean[j] = open_steps(amean[j], count);
+    }
+    __device__ __forceinline__ void close_counts(unsigned int count)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xmean[j] = close_steps(xmean[j], count);
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) amean[j] = close_steps(amean[j], count);
+    }
     // per-step means (nhood1: observer_neighborhood_1.clh:250-261)
     __device__ __forceinline__ void update_count(const Instance &I, unsigned int count)
     {
@@ -196,7 +230,7 @@ struct Extents {
         for (int j = 0; j < NV; ++j) {
             ext_max(xmax[j], I.x[j]);
             ext_min(xmin[j], I.x[j]);
-            { realtype m = xmean[j]; mean_count(&m, I.x[j], count); xmean[j] = m; }
+            { realtype m = xmean[j]; mean_steps(&m, I.x[j], count); xmean[j] = m; }
             ext_max(dxmax[j], I.k1[j]);
             ext_min(dxmin[j], I.k1[j]);
         }
@@ -204,7 +238,7 @@ struct Extents {
         for (int j = 0; j < N_AUX; ++j) {
             ext_max(amax[j], I.aux[j]);
             ext_min(amin[j], I.aux[j]);
-            { realtype m = amean[j]; mean_count(&m, I.aux[j], count); amean[j] = m; }
+            { realtype m = amean[j]; mean_steps(&m, I.aux[j], count); amean[j] = m; }
         }
     }
     // persistence visitor: through a temporary, so that it works for both placements
@@ -292,7 +326,7 @@ struct Observer {
     template <class V> __device__ __forceinline__ void visit(V &v)
     {
         v(xmax); v(xmin); v(xmean); v(dxmax); v(dxmin); v(t_last); v(t_start); v(steps);
-    }
+    }    template <class V> __device__ __forceinline__ void visit_warmup(V &) {} // one-pass observer: no warm-up loop
 };
 
 // =======================================================================================
@@ -329,7 +363,7 @@ struct Observer {
         o.put((realtype)steps);
     }
     __device__ __forceinline__ void rebase(realtype T) { t_start -= T; }
-    template <class V> __device__ __forceinline__ void visit(V &v) { ext.visit(v); v(t_last); v(t_start); v(steps); }
+    template <class V> __device__ __forceinline__ void visit(V &v) { ext.visit(v); v(t_last); v(t_start); v(steps); }    template <class V> __device__ __forceinline__ void visit_warmup(V &) {} // one-pass observer: no warm-up loop
 };
 
 // =======================================================================================
@@ -439,7 +473,7 @@ struct Observer {
         imi.visit(v); amp.visit(v);
         v(t_start); v(t_last_max); v(t_last_min); v(x_last_min);
         v(events); v(steps);
-    }
+    }    template <class V> __device__ __forceinline__ void visit_warmup(V &) {} // one-pass observer: no warm-up loop
 };
 
 // =======================================================================================
@@ -477,7 +511,7 @@ struct Observer {
         for (int j = 0; j < NV; ++j) { xb[j][0] = xb[j][1]; xb[j][1] = xb[j][2]; xb[j][2] = I.x[j]; }
         de1 = de2; de2 = I.k1[E_VAR_IX];
         df1 = df2; df2 = I.k1[F_VAR_IX];
-        step_dt.push(tb[2] - tb[1], steps);
+        step_dt.push_step(tb[2] - tb[1], steps);
         ext.update_count(I, steps);
         if (steps > 1) {
             if (!found) {
@@ -494,8 +528,9 @@ struct Observer {
             }
         }
     }
-    __device__ __forceinline__ void open_means() {}  // per-step means only
-    __device__ __forceinline__ void close_means() {}
+    // per-step means only
+    __device__ __forceinline__ void open_means() { ext.open_counts(steps); step_dt.mean = open_steps(step_dt.mean, steps); }
+    __device__ __forceinline__ void close_means() { ext.close_counts(steps); step_dt.mean = close_steps(step_dt.mean, steps); }
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2 || !found) return false;
@@ -551,7 +586,7 @@ struct Observer {
         peaks_stat.visit(v); period.visit(v); step_dt.visit(v);
         v(t_start); v(t_last_event);
         v(peaks); v(events); v(steps); v(found); v(inside);
-    }
+    }    template <class V> __device__ __forceinline__ void visit_warmup(V &) {} // one-pass observer: no warm-up loop
 };
 
 // =======================================================================================
@@ -605,7 +640,7 @@ struct Observer {
         xe1 = xe2; xe2 = I.x[E_VAR_IX];
         df1 = df2; df2 = I.k1[F_VAR_IX];
         const realtype dt = tb[2] - tb[1];
-        step_dt.push(dt, steps);
+        step_dt.push_step(dt, steps);
         ext.update_time(I, mean_weight(dt, I.t - t_start));
         if (steps < 2) return;
         if (found) {
@@ -619,8 +654,8 @@ struct Observer {
             for (int j = 0; j < NV; ++j) center[j] = I.x[j];
         }
     }
-    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); }
-    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); }
+    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); step_dt.mean = open_steps(step_dt.mean, steps); }
+    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); step_dt.mean = close_steps(step_dt.mean, steps); }
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2 || !found) return false;
@@ -682,6 +717,12 @@ struct Observer {
         v(t_start); v(t_last_event); v(x_threshold);
         v(peaks); v(found); v(inside); v(events); v(steps);
     }
+    // the fields the warm-up pass accumulates (what a parked warm-up has to carry; the rest is init()'s)
+    template <class V> __device__ __forceinline__ void visit_warmup(V &v)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { Extents::visit_one(v, ext.xmax[j]); Extents::visit_one(v, ext.xmin[j]); }
+    }
 };
 
 // =======================================================================================
@@ -739,7 +780,7 @@ struct Observer {
         xf[0] = xf[1]; xf[1] = xf[2]; xf[2] = I.x[F_VAR_IX];
         d1 = d2; d2 = I.k1[F_VAR_IX];
         const realtype dt = tb[2] - tb[1];
-        step_dt.push(dt, steps);
+        step_dt.push_step(dt, steps);
         ext.update_time(I, mean_weight(dt, I.t - t_start));
         if (steps > 1) {
             if (d1 > 0.0 && d2 < 0.0) peaks++; // local maximum of the feature variable
@@ -751,16 +792,53 @@ struct Observer {
                     t_this_down = I.t;
                     up = 0;
                     if (events > 0 && events <= N_STORE_EVENTS) list_set(t_down, events - 1, t_this_down);
+#if CLODE_INTEGRAL_MEANS
+                    down_mean = ZERO; // the integral restarts; the sample at the crossing has zero weight in the reference too
+#else
                     down_mean = I.x[F_VAR_IX];
+#endif
                 }
             } else {
                 const realtype since = I.t - t_this_down;
+#if CLODE_INTEGRAL_MEANS
+                if (since > 0.0) down_mean = fma(I.x[F_VAR_IX], dt, down_mean);
+#else
                 if (since > 0.0) down_mean = mean_step(down_mean, I.x[F_VAR_IX], dt, since);
+#endif
             }
         }
     }
-    __device__ __forceinline__ void open_means() { ext.open_means(tb[2] - t_start); }
-    __device__ __forceinline__ void close_means() { ext.close_means(tb[2] - t_start); }
+    // down_mean: the time-weighted mean of x[fVar] since the last downward crossing.  The reference's recurrence
+    // m += (x - m) dt / (t - t_down) is, multiplied by (t - t_down), the integral S += x dt (t - dt is the previous
+    // sample's time), with S = 0 at a crossing; the mean is only READ when the next event fires.  Production build:
+    // one FMA per step instead of a division, the quotient once per event (down_mean_now) and on exit.
+    __device__ __forceinline__ void open_means()
+    {
+        ext.open_means(tb[2] - t_start);
+        step_dt.mean = open_steps(step_dt.mean, steps);
+#if CLODE_INTEGRAL_MEANS
+        const realtype since = tb[2] - t_this_down;
+        if (since > ZERO) down_mean *= since;
+#endif
+    }
+    __device__ __forceinline__ void close_means()
+    {
+        ext.close_means(tb[2] - t_start);
+        step_dt.mean = close_steps(step_dt.mean, steps);
+#if CLODE_INTEGRAL_MEANS
+        const realtype since = tb[2] - t_this_down;
+        if (since > ZERO) down_mean /= since;
+#endif
+    }
+    __device__ __forceinline__ realtype down_mean_now(realtype now) const
+    {
+#if CLODE_INTEGRAL_MEANS
+        const realtype since = now - t_this_down;
+        return since > ZERO ? down_mean / since : down_mean;
+#else
+        return down_mean;
+#endif
+    }
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2) return false;
@@ -782,7 +860,7 @@ struct Observer {
             up_time.push(this_up, n);
             down_time.push(now - t_this_down, n);
             duty.push(this_up / this_period, n);
-            dip.push(down_mean - x_last_min, n);
+            dip.push(down_mean_now(now) - x_last_min, n);
         }
         if (events <= N_STORE_EVENTS) list_set(t_up, events - 1, now);
         t_last_event = now;
@@ -830,6 +908,8 @@ struct Observer {
         v(t_start); v(t_last_event); v(t_this_down); v(x_last_min);
         v(peaks); v(steps); v(events); v(up);
     }
+    // the fields the warm-up pass accumulates (what a parked warm-up has to carry; the rest is init()'s)
+    template <class V> __device__ __forceinline__ void visit_warmup(V &v) { v(g_xmax); v(g_xmin); v(g_dxmax); v(g_dxmin); }
 };
 
 #else

@@ -402,6 +402,10 @@ struct KernelArgs {
     unsigned int row_begin, row_end, resume;
     unsigned int block_order;
     CUdeviceptr cost_in, cost_out;
+    CUdeviceptr perm;
+    unsigned long long n_slots;
+    unsigned int attempt_budget, sched_resume;
+    CUdeviceptr park_real, park_uint, sched_state;
 };
 
 std::string cu_error(DriverApi *d, CUresult r)
@@ -443,6 +447,11 @@ struct clode_sim {
     size_t real_size = 8;
     Buffer x0, pars, xf, rng, dt, tf, steps, od_real, od_uint, F, tr_t, tr_x, tr_dx, tr_aux, n_stored, queue;
     Buffer cost; // 2 x 2 u64: accepted steps in the lower / upper half of the ensemble (block_order auto)
+    // cost-sorted chunked execution of the adaptive time loops (kernels.cuh "Scheduling")
+    Buffer park_real, park_uint, perm[2], sched_bucket, sched_hist, sched_cursor, sched_state;
+    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr;
+    int perm_cur = 0;
+    bool warmup_costs_fresh = false; // park_uint holds the step counts of a warm-up pass over the current problem
     size_t tr_rows = 0; // allocated trajectory rows (max_store + 1)
     // streamed trajectory: two chunk buffer sets (one integrates while the other is copied out) + resume state
     struct Chunk { Buffer t, x, dx, aux; } chunk[2];
@@ -529,10 +538,11 @@ struct clode_sim {
     void free_ensemble()
     {
         Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue, &cost,
+                         &park_real, &park_uint, &perm[0], &perm[1], &sched_bucket, &sched_hist, &sched_cursor, &sched_state,
                          &chunk[0].t, &chunk[0].x, &chunk[0].dx, &chunk[0].aux, &chunk[1].t, &chunk[1].x, &chunk[1].dx, &chunk[1].aux,
                          &rs_real, &rs_uint, &chunk_flags};
         for (Buffer *b : all) release(*b);
-        n = 0; tr_rows = 0; observer_initialized = false;
+        n = 0; tr_rows = 0; observer_initialized = false; warmup_costs_fresh = false;
     }
 
     KernelArgs args() const
@@ -552,6 +562,7 @@ struct clode_sim {
         a.tr_t = tr_t.ptr; a.tr_x = tr_x.ptr; a.tr_dx = tr_dx.ptr; a.tr_aux = tr_aux.ptr;
         a.n_stored = n_stored.ptr; a.queue = queue.ptr;
         a.row_begin = 0; a.row_end = 0xffffffffu; a.resume = 0; // one launch stores every row
+        a.attempt_budget = 0xffffffffu;                         // ... and runs every instance to completion
         return a;
     }
 
@@ -618,7 +629,7 @@ struct clode_sim {
         unsigned grid = 1;
         if ((rc = grid_for(f, grid))) return rc;
         KernelArgs a = a_in;
-        a.block_order = block_order_mode();
+        a.block_order = a.park_real ? 0u : block_order_mode(); // a sorted order is already longest-first
         // initializeObserver of a one-pass observer has no time loop: it neither uses nor replaces the history
         if (a.block_order == 2 && f == k_init && !two_pass) a.block_order = 0;
         if (a.block_order == 2 && cost.ptr) {
@@ -639,6 +650,109 @@ struct clode_sim {
             if ((rc = cu(d->cuEventRecord(ev1, stream), "cuEventRecord"))) return rc;
             pending = true;
             if (blocking) return wait(what);
+        }
+        return CLODE_OK;
+    }
+
+    // ---- cost-sorted chunked execution of an adaptive time loop (device/kernels.cuh "Scheduling") -----------------
+    // Enqueued as ONE stream-ordered sequence without host round trips: the scan kernel leaves the number of live
+    // instances and the next attempt budget in device memory (sched_state), the time-loop kernel reads them, and
+    // surplus blocks of the full-size grid exit at once.  CLODE_SCHED=off disables it;
+    // CLODE_SCHED="pilot,rounds,fraction,min" overrides the schedule (defaults 256, 8, 0.5, 256).
+    struct Schedule {
+        bool on = true;
+        unsigned pilot = 256, rounds = 8, budget_min = 256;
+        float fraction = 0.5f;
+    };
+    Schedule schedule() const
+    {
+        Schedule sc;
+        // only the adaptive steppers diverge; persistent-thread builds balance themselves
+        sc.on = (spec.stepper == 3 || spec.stepper == 4) && !spec.work_queue && k_sched_hist && k_sched_scan && k_sched_scatter;
+        if (const char *env = std::getenv("CLODE_SCHED")) {
+            if (std::strcmp(env, "off") == 0 || std::strcmp(env, "0") == 0) sc.on = false;
+            else std::sscanf(env, "%u,%u,%f,%u", &sc.pilot, &sc.rounds, &sc.fraction, &sc.budget_min);
+        }
+        if (sc.rounds < 1) sc.rounds = 1;
+        if (sc.pilot < 1) sc.pilot = 1;
+        if (n >= 0xffffffffull) sc.on = false; // instance indices travel as 32-bit words
+        return sc;
+    }
+
+    int ensure_sched_buffers()
+    {
+        int rc;
+        const size_t rows = 2 * (size_t)spec.n_var + (size_t)std::max(spec.n_aux, 1) + 3;
+        if ((rc = alloc(park_real, real_size * rows * n, "parked state"))) return rc;
+        if ((rc = alloc(park_uint, 4 * 2 * n, "parked state"))) return rc;
+        if ((rc = alloc(perm[0], 4 * n, "instance order"))) return rc;
+        if ((rc = alloc(perm[1], 4 * n, "instance order"))) return rc;
+        if ((rc = alloc(sched_bucket, 4 * n, "scheduler buckets"))) return rc;
+        if ((rc = alloc(sched_hist, 4 * 1024, "scheduler histogram"))) return rc;
+        if ((rc = alloc(sched_cursor, 4 * 1024, "scheduler cursors"))) return rc;
+        if ((rc = alloc(sched_state, 32, "scheduler state"))) return rc;
+        return CLODE_OK;
+    }
+
+    // Sort the live instances of the order `perm_in` (null: all n, identity) into perm[perm_cur ^ 1].  The slot count of
+    // the order being re-sorted is what the previous sort's scan left in `state_in` (device memory; null: n), and this
+    // sort's scan leaves {live instances, dearest bucket, next budget} in `state_out`.
+    int sort_id = 0;
+    CUdeviceptr sched_state_slot(int k) const { return sched_state.ptr + 16 * (size_t)(k & 1); }
+    int enqueue_sort(CUdeviceptr perm_in, CUdeviceptr state_in, CUdeviceptr state_out, unsigned by_steps, const Schedule &sc)
+    {
+        int rc;
+        if ((rc = cu(d->cuMemsetD8Async(sched_hist.ptr, 0, sched_hist.bytes, stream), "scheduler: clear histogram"))) return rc;
+        const unsigned block = 256, grid = (unsigned)((n + block - 1) / block);
+        unsigned long long nn = n;
+        CUdeviceptr out = perm[perm_cur ^ 1].ptr;
+        double t0_ = t0, t1_ = t1;
+        void *hp[] = {&perm_in, &state_in, &nn, &park_real.ptr, &park_uint.ptr, &t0_, &t1_, &by_steps, &sched_bucket.ptr, &sched_hist.ptr};
+        if ((rc = cu(d->cuLaunchKernel(k_sched_hist, grid, 1, 1, block, 1, 1, 0, stream, hp, nullptr), "clode_sched_histogram"))) return rc;
+        float fraction = sc.fraction;
+        unsigned budget_min = sc.budget_min;
+        void *sp_[] = {&sched_hist.ptr, &sched_cursor.ptr, &state_out, &fraction, &budget_min};
+        if ((rc = cu(d->cuLaunchKernel(k_sched_scan, 1, 1, 1, 1024, 1, 1, 0, stream, sp_, nullptr), "clode_sched_scan"))) return rc;
+        void *cp[] = {&perm_in, &state_in, &nn, &sched_bucket.ptr, &sched_cursor.ptr, &out};
+        if ((rc = cu(d->cuLaunchKernel(k_sched_scatter, grid, 1, 1, block, 1, 1, 0, stream, cp, nullptr), "clode_sched_scatter"))) return rc;
+        launches += 3;
+        perm_cur ^= 1;
+        return CLODE_OK;
+    }
+
+    // `f` over the ensemble as pilot + sorted rounds (or, with exact costs from a previous pass in park_uint, one
+    // sorted launch); falls back to the plain launch when scheduling does not apply
+    int run_loop(CUfunction f, const char *what, bool first, bool last, bool blocking, bool costs_known = false)
+    {
+        const Schedule sc = schedule();
+        const bool has_loop = !(f == k_init && !two_pass);
+        if (!sc.on || !has_loop || n == 0) return launch(f, what, first, last, blocking);
+        int rc;
+        if ((rc = ensure_sched_buffers())) return rc;
+        KernelArgs a = args();
+        a.park_real = park_real.ptr; a.park_uint = park_uint.ptr;
+        if (costs_known) { // exact longest-first order, one launch to completion
+            if (first && (rc = cu(d->cuEventRecord(ev0, stream), "cuEventRecord"))) return rc;
+            if ((rc = enqueue_sort(0, 0, sched_state_slot(0), 1u, sc))) return rc;
+            a.perm = perm[perm_cur].ptr;
+            a.n_slots = n;
+            warmup_costs_fresh = false;
+            return launch_with(f, a, what, false, last, blocking);
+        }
+        // pilot: caller's order, fixed budget
+        a.attempt_budget = sc.pilot;
+        if ((rc = launch_with(f, a, what, first, false, false))) return rc;
+        warmup_costs_fresh = false;
+        CUdeviceptr prev = 0;
+        for (unsigned r = 0; r < sc.rounds; ++r) {
+            if ((rc = enqueue_sort(prev, r > 0 ? sched_state_slot((int)r - 1) : 0, sched_state_slot((int)r), 0u, sc))) return rc;
+            prev = perm[perm_cur].ptr;
+            a.perm = prev;
+            a.sched_state = sched_state_slot((int)r);
+            a.sched_resume = 1;
+            a.attempt_budget = (r + 1 == sc.rounds) ? 0xffffffffu : 0u; // last round: to completion; else the device-side budget
+            const bool final_round = r + 1 == sc.rounds;
+            if ((rc = launch_with(f, a, what, false, last && final_round, blocking && final_round))) return rc;
         }
         return CLODE_OK;
     }
@@ -875,6 +989,10 @@ static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<
     if (spec.kernels & CLODE_KERNEL_TRAJECTORY) {
         if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_trajectory, s->module, "clode_trajectory"), "clode_trajectory"))) return rc;
     }
+    s->k_sched_hist = s->k_sched_scan = s->k_sched_scatter = nullptr;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_hist, s->module, "clode_sched_histogram"), "clode_sched_histogram"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scan, s->module, "clode_sched_scan"), "clode_sched_scan"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scatter, s->module, "clode_sched_scatter"), "clode_sched_scatter"))) return rc;
     // per-thread local memory (spills + stack) of each time-loop kernel; -1 = kernel not in this program
     CUfunction loops[4] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory};
     for (int k = 0; k < 4; ++k) {
@@ -1131,7 +1249,7 @@ static int run_transient(clode_sim *s, bool blocking)
     if (!s) return fail(CLODE_ERR_INVALID, "sim is null");
     if (!s->built) return fail(CLODE_ERR_STATE, "transient: program not built");
     clode_sim::Scope scope(s);
-    return s->launch(s->k_transient, "clode_transient", true, true, blocking);
+    return s->run_loop(s->k_transient, "clode_transient", true, true, blocking);
 }
 int clode_sim_transient(clode_sim *s) { return run_transient(s, true); }
 
@@ -1158,8 +1276,11 @@ int clode_sim_initialize_observer(clode_sim *s)
     clode_sim::Scope scope(s);
     int rc = ensure_feature_buffers(s);
     if (rc) return rc;
-    rc = s->launch(s->k_init, "clode_initialize_observer", true, true);
-    if (!rc) s->observer_initialized = true;
+    rc = s->run_loop(s->k_init, "clode_initialize_observer", true, true, true);
+    if (!rc) {
+        s->observer_initialized = true;
+        s->warmup_costs_fresh = s->two_pass && s->schedule().on;
+    }
     return rc;
 }
 
@@ -1177,11 +1298,13 @@ static int run_features(clode_sim *s, int initialize, bool blocking)
     // both launches are inside the timed region
     bool first = true;
     if (!s->observer_initialized) {
-        if ((rc = s->launch(s->k_init, "clode_initialize_observer", true, false))) return rc;
+        if ((rc = s->run_loop(s->k_init, "clode_initialize_observer", true, false, false))) return rc;
         s->observer_initialized = true;
+        s->warmup_costs_fresh = s->two_pass && s->schedule().on;
         first = false;
     }
-    return s->launch(s->k_features, "clode_features", first, true, blocking);
+    // right after a warm-up pass over the same trajectories its step counts are the exact costs of this pass
+    return s->run_loop(s->k_features, "clode_features", first, true, blocking, s->warmup_costs_fresh && initialize != 0);
 }
 
 int clode_sim_observer_initialized(clode_sim *s, int *flag)

@@ -40,7 +40,9 @@ class KernelArgs(ctypes.Structure):
                                         "tr_t", "tr_x", "tr_dx", "tr_aux", "n_stored", "queue",
                                         "rs_real", "rs_uint", "chunk_flags")] + [
         ("row_begin", ctypes.c_uint), ("row_end", ctypes.c_uint), ("resume", ctypes.c_uint), ("block_order", ctypes.c_uint),
-        ("cost_in", ctypes.c_void_p), ("cost_out", ctypes.c_void_p)]
+        ("cost_in", ctypes.c_void_p), ("cost_out", ctypes.c_void_p),
+        ("perm", ctypes.c_void_p), ("n_slots", ctypes.c_ulonglong), ("attempt_budget", ctypes.c_uint), ("sched_resume", ctypes.c_uint),
+        ("park_real", ctypes.c_void_p), ("park_uint", ctypes.c_void_p), ("sched_state", ctypes.c_void_p)]
 
 
 def _ptr(a):
@@ -98,6 +100,7 @@ class EmuLib:
             a.op_eps_dx = op.eps_dx
         a.n = n
         a.row_begin, a.row_end, a.resume = 0, 0xFFFFFFFF, 0
+        a.attempt_budget = 0xFFFFFFFF
         a.block_order = getattr(self, "block_order", 0)
         for k, v in bufs.items():
             setattr(a, k, _ptr(v) if v is not None else None)
@@ -136,6 +139,53 @@ class EmuLib:
         a = self._args(tspan, sp, op, n, dict(b, od_real=self.od_real, od_uint=self.od_uint, F=F))
         self.lib.emu_features(ctypes.byref(a))
         return dict(F=F, xf=b["xf"], tf=b["tf"], dt=b["dt"], rng=b["rng"], steps=b["steps"])
+
+    # ---- the chunked (scheduled) time loops, driven the way clode_rt.cpp's run_loop drives them -----------------
+    def _chunked(self, kernel, a, n, budgets, seed):
+        """pilot + rounds: after every launch the unfinished instances are re-ordered (here: randomly — the result must
+        not depend on the order) and continued with the next attempt budget; the last round runs to completion"""
+        nv, na = self.n_var, max(self.n_aux, 1)
+        park_real = np.zeros((2 * nv + na + 3) * n, self.real)
+        park_uint = np.zeros(2 * n, np.uint32)
+        a.park_real, a.park_uint = _ptr(park_real), _ptr(park_uint)
+        rng = np.random.default_rng(seed)
+        a.attempt_budget, a.sched_resume, a.perm, a.n_slots = budgets[0], 0, None, 0
+        kernel(ctypes.byref(a))
+        launches = 1
+        for k, budget in enumerate(list(budgets[1:]) + [0xFFFFFFFF]):
+            live = np.flatnonzero((park_uint[n:] & 2) == 0).astype(np.uint32)
+            if live.size == 0:
+                break
+            perm = rng.permutation(live).astype(np.uint32)
+            a.perm, a.n_slots, a.attempt_budget, a.sched_resume = _ptr(perm), perm.size, budget, 1
+            kernel(ctypes.byref(a))
+            launches += 1
+        assert np.all(park_uint[n:] & 2), "instances left unfinished"
+        return launches, park_uint[:n].copy()
+
+    def transient_chunked(self, tspan, x0, pars, sp, dt, rng, budgets=(7, 50, 300), seed=0):
+        n = len(dt)
+        b = self._prep(x0, pars, dt, rng, n)
+        a = self._args(tspan, sp, None, n, b)
+        launches, _ = self._chunked(self.lib.emu_transient, a, n, budgets, seed)
+        return dict(xf=b["xf"], tf=b["tf"], dt=b["dt"], rng=b["rng"], steps=b["steps"], launches=launches)
+
+    def features_chunked(self, tspan, x0, pars, sp, op, dt, rng, budgets=(7, 50, 300), seed=0):
+        n = len(dt)
+        b = self._prep(x0, pars, dt, rng, n)
+        self.od_real = np.zeros(max(1, self.od_nreal * n), self.real)
+        self.od_uint = np.zeros(max(1, self.od_nuint * n), np.uint32)
+        a = self._args(tspan, sp, op, n, dict(b, od_real=self.od_real, od_uint=self.od_uint))
+        launches = 1
+        if self.two_pass:
+            launches, warm_steps = self._chunked(self.lib.emu_initialize_observer, a, n, budgets, seed)
+        else:
+            self.lib.emu_initialize_observer(ctypes.byref(a))
+        b = self._prep(x0, pars, dt, rng, n)
+        F = np.zeros(self.n_feat * n, self.real)
+        a = self._args(tspan, sp, op, n, dict(b, od_real=self.od_real, od_uint=self.od_uint, F=F))
+        k, _ = self._chunked(self.lib.emu_features, a, n, budgets, seed + 1)
+        return dict(F=F, xf=b["xf"], tf=b["tf"], dt=b["dt"], rng=b["rng"], steps=b["steps"], launches=launches + k)
 
     def trajectory(self, tspan, x0, pars, sp, dt, rng, nthreads=1):
         n = len(dt)

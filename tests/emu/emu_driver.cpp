@@ -23,7 +23,8 @@ static void run(void (*kernel)(), const KernelArgs *a)
 {
     clode_args = *a;
     const unsigned block = CLODE_BLOCK;
-    const unsigned grid = (unsigned)((a->n + block - 1) / block);
+    const size_t slots = a->n_slots ? (size_t)a->n_slots : (size_t)a->n;
+    const unsigned grid = (unsigned)((slots + block - 1) / block);
     blockDim.x = block;
     gridDim.x = grid;
     for (unsigned b = 0; b < grid; ++b)

@@ -131,3 +131,52 @@ def test_block_order_only_permutes_the_schedule(order):
     got = lib.features((0.0, 2.0), x0, pars, sp, Observer(), dt, rng)
     lib.block_order = 0
     assert_bit_equal(got, want, f"block_order={order}")
+
+
+@pytest.mark.parametrize("model, stepper, observer, n_store, tspan", [
+    ("lorenz63", "dopri5", "basic", 0, (0.0, 6.0)),
+    ("lorenz63", "dopri5", "localmax", 2, (0.0, 6.0)),
+    ("lorenz63", "bs23", "nhood1", 0, (0.0, 6.0)),
+    ("lorenz63", "bs23", "nhood2", 2, (0.0, 6.0)),       # two-pass: the warm-up pass is chunked as well
+    ("lactotroph", "bs23", "thresh2", 2, (0.0, 600.0)),  # C3's kernel pair
+    ("vanderpol", "dopri5", "thresh2", 0, (0.0, 30.0)),
+    ("lactotroph", "dopri5", "basicall", 0, (0.0, 300.0)),
+])
+@pytest.mark.parametrize("math, contract", [("pm", "off"), ("libm", "fast")])
+def test_scheduled_time_loop_is_bit_identical_to_one_launch(model, stepper, observer, n_store, tspan, math, contract):
+    """Cost-sorted chunked execution (kernels.cuh "Scheduling", clode_rt.cpp run_loop): a time loop cut into launches
+    of bounded attempt budget, with the unfinished instances re-ordered arbitrarily in between, parks and resumes every
+    instance without changing a bit of its results — features, accepted-step counts, final state, dt — in the bit-exact
+    arithmetic and under FMA contraction alike (the FSAL slope is stored, never recomputed)."""
+    cfg = Config(model, stepper, observer, n_store, math=math, contract=contract)
+    lib = EmuLib(cfg)
+    n = 2 * 128 + 19
+    _, x0, pars = ensemble(model, n)
+    sp = Solver(dt=0.01, dtmax=1.0 if model != "lactotroph" else 50.0, abstol=1e-6, reltol=1e-5, max_steps=100000)
+    op = Observer(max_event_count=50, max_event_timestamps=n_store, x_up_threshold=0.3, x_down_threshold=0.2)
+    dt, rng = np.full(n, sp.dt), seed_states(1, n)
+    want = lib.features(tspan, x0, pars, sp, op, dt, rng)
+    for budgets, seed in (((1,), 0), ((7, 50, 300), 1), ((64, 64, 64, 64, 64, 64), 2)):
+        got = lib.features_chunked(tspan, x0, pars, sp, op, dt, rng, budgets=budgets, seed=seed)
+        assert got.pop("launches") >= 2
+        assert_bit_equal(got, want, f"{model}/{stepper}/{observer} {math} budgets={budgets}")
+    want_t = lib.transient(tspan, x0, pars, sp, dt, rng)
+    got_t = lib.transient_chunked(tspan, x0, pars, sp, dt, rng, budgets=(5, 40, 200), seed=3)
+    got_t.pop("launches")
+    assert_bit_equal(got_t, want_t, f"{model}/{stepper} transient {math}")
+
+
+def test_scheduled_time_loop_handles_max_steps_and_empty_rounds():
+    """an instance that stops on max_steps (not on t_end) finishes inside a round like any other; rounds that find
+    nothing left to do are harmless"""
+    cfg = Config("lorenz63", "dopri5", "basic", math="pm")
+    lib = EmuLib(cfg)
+    n = 70
+    _, x0, pars = ensemble("lorenz63", n)
+    sp = Solver(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-6, max_steps=333)
+    dt, rng = np.full(n, sp.dt), seed_states(1, n)
+    want = lib.features((0.0, 50.0), x0, pars, sp, Observer(), dt, rng)
+    got = lib.features_chunked((0.0, 50.0), x0, pars, sp, Observer(), dt, rng, budgets=(100, 100, 100, 100, 100))
+    got.pop("launches")
+    assert_bit_equal(got, want, "max_steps cut-off")
+    assert got["steps"].max() == 333
