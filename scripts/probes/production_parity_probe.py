@@ -32,6 +32,36 @@ def main():
     from oracle.common import Config, Observer, Solver
 
     build.build_runtime()
+    if "C5" in args.workloads:
+        args.workloads.remove("C5")
+        n = args.npts or (1 << 18)
+        w = bench.workload("C5", n, np.arange(n))
+        nv, npar, na, nw = MODELS[w["model"]]
+        sub = np.sort(np.random.default_rng(7).choice(n, 256, replace=False))
+        x0s, ps = sharding.take_rows(w["x0"], nv, n, sub), sharding.take_rows(w["pars"], npar, n, sub)
+        prog = _rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, kernels=_rt.KERNEL_TRAJECTORY)
+        sim = _rt.Sim(prog)
+        sim.set_solver_params(**w["solver"])
+        sim.set_tspan(*w["tspan"])
+        sim.set_problem(x0s, ps)
+        sim.seed_rng(1)
+        sim.trajectory()
+        tr = sim.get_trajectory()
+        rows = w["solver"]["max_store"]
+        lib = restate.OracleLib(Config(w["model"], w["stepper"], math="libm"))
+        sp = Solver(**w["solver"])
+        o = lib.trajectory(w["tspan"], x0s, ps, sp, np.full(sub.size, sp.dt), sharding.seed_states_for(1, n, sub))
+        m = sub.size
+        xg = np.asarray(tr["x"]).reshape(-1, nv, m)[:rows]
+        xo = np.asarray(o["x"]).reshape(-1, nv, m)[:rows]
+        scale = np.abs(xo).max(axis=(0, 2), keepdims=True)
+        dev = np.abs(xg - xo) / scale
+        print(json.dumps({"workload": "C5", "sampled": m, "n_stored_identical": bool(np.array_equal(tr["n_stored"], o["n_stored"])),
+                          "t_identical": bool(np.array_equal(np.asarray(tr["t"])[:rows * m], np.asarray(o["t"])[:rows * m])),
+                          "max_dev_rows_0_200": float(dev[:200].max()), "max_dev_rows_0_1000": float(dev[:1000].max()),
+                          "max_dev_all": float(dev.max()), "median_final_dev": float(np.median(dev[-1])),
+                          "p99_all": float(np.quantile(dev, 0.99))}), flush=True)
+        sim.close()
     for name in args.workloads:
         n = args.npts or {"C4": 1 << 22, "C5": 1 << 18}.get(name, 1 << 20)
         w = bench.workload(name, n, np.arange(n))

@@ -1,0 +1,123 @@
+"""Parity of the PRODUCTION tier — the default build, the one bench.py times — at the BASELINE.json sizes.
+
+The production build differs from the reference arithmetic (the oracle compiled without FMA contraction) by: FMA
+contraction (which OpenCL C allows any device compiler by default, so the reference itself runs contracted on a GPU),
+the controller's root and the error norm's reciprocal from SFU seeds (<= 2 ulp / < 1e-11), means carried as integrals,
+the engine's exp (<= 0.52 ulp).  None of that can be bit-identical to a CPU build, so the statement tested here is:
+
+  * where the dynamics forgets perturbations (Lorenz below the onset of transient chaos, r < 13.9) the accepted-step
+    counts are IDENTICAL to the reference arithmetic's and the features agree to 1e-9;
+  * everywhere else the production tier is no further from the reference arithmetic than FMA contraction alone is:
+    the oracle is built a second time with -ffp-contract=fast and its distance from the uncontracted oracle is the
+    yardstick (same instances, same test);
+  * on chaotic instances (r > 24.74) only distributions are comparable.
+
+Measured on B200 (scripts/probes/production_parity_probe.py, round 2, 2048 sampled instances): C2 r < 13.9: 448 of
+448 identical step counts, features within 5.4e-11; 13.9 < r < 24.06: 96.9 % identical; C3: event counts identical on
+100 %, step counts on 93.2 % (contraction alone: 92.8 %), largest step-count difference 1.2 %.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate
+from oracle.common import MODELS, Config, Observer, Solver
+from clode_b200 import sharding
+from problems import rhs_source
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+def _production_run(rt, name, n):
+    import bench
+
+    w = bench.workload(name, n, np.arange(n))
+    nv, npar, na, nw = MODELS[w["model"]]
+    prog = rt.Program(rhs_source(w["model"]), w["stepper"], nv, npar, na, nw, observer=w["observer"], kernels=rt.KERNEL_FEATURES)
+    sim = rt.Sim(prog)
+    sim.set_solver_params(**w["solver"])
+    sim.set_observer_params(**w["observer_params"])
+    sim.set_tspan(*w["tspan"])
+    sim.set_problem(w["x0"], w["pars"])
+    sim.seed_rng(1)
+    sim.features(1)
+    nf = sim.n_features()
+    out = dict(F=sim.get_f().reshape(nf, n), xf=sim.get_xf().reshape(nv, n), steps=sim.get_steps().astype(np.int64))
+    sim.close()
+    return w, out
+
+
+def _oracle(w, n, sub, contract):
+    nv, npar = MODELS[w["model"]][:2]
+    lib = restate.OracleLib(Config(w["model"], w["stepper"], w["observer"], math="libm", contract=contract))
+    sp, op = Solver(**w["solver"]), Observer(**w["observer_params"])
+    o = lib.features(w["tspan"], sharding.take_rows(w["x0"], nv, n, sub), sharding.take_rows(w["pars"], npar, n, sub), sp, op,
+                     np.full(sub.size, sp.dt), sharding.seed_states_for(1, n, sub), nthreads=CORES)
+    return o["F"].reshape(-1, sub.size), o["xf"].reshape(nv, sub.size)
+
+
+def test_c2_production_tier_vs_reference_arithmetic_2e20(rt):
+    n = 1 << 20
+    w, g = _production_run(rt, "C2", n)
+    assert np.array_equal(g["F"][5], g["steps"].astype(np.float64))
+    sub = np.sort(np.random.default_rng(11).choice(n, 768, replace=False))
+    r = w["pars"].reshape(3, n)[0, sub]
+    Fo, xo = _oracle(w, n, sub, "off")     # the reference arithmetic
+    Fc, _ = _oracle(w, n, sub, "fast")     # the same code, FMA-contracted by gcc: the yardstick
+    Fg, xg = g["F"][:, sub], g["xf"][:, sub]
+    same_gpu, same_fma = Fg[5] == Fo[5], Fc[5] == Fo[5]
+
+    calm = r < 13.9  # the trajectory spirals into a fixed point without a chaotic transient: perturbations decay
+    assert calm.sum() > 100
+    assert same_gpu[calm].all(), f"accepted-step counts differ on {np.count_nonzero(~same_gpu[calm])} of {calm.sum()} calm instances"
+    scale = np.abs(Fo[:5, calm]).max(axis=1, keepdims=True)
+    assert (np.abs(Fg[:5, calm] - Fo[:5, calm]) / scale).max() < 1e-9
+    np.testing.assert_allclose(xg[:, calm], xo[:, calm], rtol=1e-8, atol=1e-9)
+
+    transient_chaos = (r >= 13.9) & (r < 24.06)
+    assert same_gpu[transient_chaos].mean() >= same_fma[transient_chaos].mean() - 0.05
+    assert same_gpu[transient_chaos].mean() > 0.85
+
+    chaotic = r > 24.74  # e^{0.9 t} error growth over t = 100: only distributions are comparable
+    so, sg = Fo[5, chaotic], Fg[5, chaotic]
+    assert abs(sg.mean() / so.mean() - 1.0) < 5e-3
+    for q in (0.1, 0.5, 0.9):
+        assert abs(np.quantile(sg, q) / np.quantile(so, q) - 1.0) < 1e-2
+    for row in (0, 1, 2):  # max, min, mean of x
+        assert abs(Fg[row, chaotic].mean() - Fo[row, chaotic].mean()) < 2e-2 * np.abs(Fo[row, chaotic]).mean() + 0.05
+    # and nowhere is the step count further from the reference's than contraction alone puts it
+    rel_gpu = np.abs(Fg[5] - Fo[5]) / Fo[5]
+    rel_fma = np.abs(Fc[5] - Fo[5]) / Fo[5]
+    assert rel_gpu.max() < max(2.0 * rel_fma.max(), 0.02)
+
+
+def test_c3_production_tier_vs_reference_arithmetic_1024x1024(rt):
+    n = 1 << 20
+    w, g = _production_run(rt, "C3", n)
+    nf = g["F"].shape[0]
+    steps_row, events_row = nf - 4, nf - 5
+    assert np.array_equal(g["F"][steps_row], g["steps"].astype(np.float64))
+    sub = np.sort(np.random.default_rng(12).choice(n, 768, replace=False))
+    Fo, _ = _oracle(w, n, sub, "off")
+    Fc, _ = _oracle(w, n, sub, "fast")
+    Fg = g["F"][:, sub]
+    # event (spike / burst) counts: identical
+    assert (Fg[events_row] == Fo[events_row]).mean() >= min(0.99, (Fc[events_row] == Fo[events_row]).mean())
+    # accepted-step counts: as often identical as under contraction alone, and never far
+    same_gpu, same_fma = (Fg[steps_row] == Fo[steps_row]).mean(), (Fc[steps_row] == Fo[steps_row]).mean()
+    assert same_gpu >= same_fma - 0.05 and same_gpu > 0.80, (same_gpu, same_fma)
+    rel_gpu = np.abs(Fg[steps_row] - Fo[steps_row]) / Fo[steps_row]
+    rel_fma = np.abs(Fc[steps_row] - Fo[steps_row]) / Fo[steps_row]
+    assert rel_gpu.max() < max(2.0 * rel_fma.max(), 0.02), (rel_gpu.max(), rel_fma.max())
+    # every feature: the 99th percentile of the deviation stays within 3x of what contraction alone causes
+    scale = np.maximum(np.abs(Fo).max(axis=1, keepdims=True), 1e-300)
+    dev_gpu = np.quantile(np.abs(Fg - Fo) / scale, 0.99, axis=1)
+    dev_fma = np.quantile(np.abs(Fc - Fo) / scale, 0.99, axis=1)
+    worst = np.argmax(dev_gpu - 3.0 * dev_fma)
+    assert np.all(dev_gpu <= 3.0 * dev_fma + 1e-6), (int(worst), float(dev_gpu[worst]), float(dev_fma[worst]))
+    # where both counts agree the solution features (extents and means of V) agree to the solver's tolerance
+    both = (Fg[events_row] == Fo[events_row]) & (Fg[steps_row] == Fo[steps_row])
+    v = slice(18, 21)  # xmax, xmin, xmean of the membrane potential
+    assert np.abs(Fg[v][:, both] - Fo[v][:, both]).max() < 50 * w["solver"]["reltol"] * np.abs(Fo[v]).max()
