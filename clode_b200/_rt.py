@@ -314,6 +314,19 @@ class Sim:
         _check(self._lib.clode_sim_get(self._h, which, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(count)))
         return out[:count] if out.size != count else out
 
+    def set_rows(self, which: int, host: np.ndarray, rows: int, pitch: int, first: int = 0, stride: int = 1):
+        """clode_sim_set_rows: element (row r, local column k) is host.flat[r*pitch + first + k*stride]"""
+        host = np.asarray(host)
+        assert host.dtype == np.float64 and host.flags.c_contiguous
+        _check(self._lib.clode_sim_set_rows(self._h, which, host.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(rows),
+                                            ctypes.c_size_t(pitch), ctypes.c_size_t(first), ctypes.c_size_t(stride)))
+
+    def get_rows(self, which: int, host: np.ndarray, rows: int, pitch: int, first: int = 0, stride: int = 1):
+        assert host.dtype == np.float64 and host.flags.c_contiguous
+        _check(self._lib.clode_sim_get_rows(self._h, which, host.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(rows),
+                                            ctypes.c_size_t(pitch), ctypes.c_size_t(first), ctypes.c_size_t(stride)))
+        return host
+
     def get_x0(self): return self.get(BUF_X0, self.n * self.prog.n_var)
     def get_xf(self, out=None): return self.get(BUF_XF, self.n * self.prog.n_var, out)
     def get_dt(self): return self.get(BUF_DT, self.n)
@@ -388,3 +401,14 @@ class Sim:
         info = KernelInfoC()
         _check(self._lib.clode_sim_kernel_info(self._h, kernel, ctypes.byref(info)))
         return {n: getattr(info, n) for n, _ in KernelInfoC._fields_}
+
+
+def gather_rows(sims, which: int, rows: int, n_total: int, out: np.ndarray | None = None) -> np.ndarray:
+    """clode_gather_rows: interleaved shards `sims` (shard g = instances g, g+G, ...) -> host [rows][n_total] through one
+    NVLink gather to sims[0]'s GPU and one device-to-host copy"""
+    if out is None:
+        out = pinned_empty(rows * n_total, device=0)
+    handles = (ctypes.c_void_p * len(sims))(*[s._h for s in sims])
+    _check(lib().clode_gather_rows(handles, len(sims), which, ctypes.c_size_t(rows), ctypes.c_size_t(n_total),
+                                   out.ctypes.data_as(ctypes.c_void_p)))
+    return out

@@ -503,6 +503,21 @@ clode_sched_scatter(const unsigned int *perm_in, const unsigned int *slots_dev, 
     __syncthreads();
     if (b != 0xffffffffu) perm_out[h[b] + rank] = inst;
 }
+
+// last step of the NVLink gather (clode_gather_rows): a shard's [rows][count] block, already on the root GPU, into the
+// global array at instances first, first + stride, ... — variable-major [rows][n_total] (the API layout) or, for the
+// Python front end's record arrays, instance-major [n_total][rows]
+extern "C" __global__ void __launch_bounds__(256)
+clode_interleave_rows(realtype *dst, const realtype *src, const unsigned long long rows, const unsigned long long count,
+                      const unsigned long long n_total, const unsigned long long first, const unsigned long long stride,
+                      const unsigned int instance_major)
+{
+    const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const size_t inst = first + j * stride;
+    for (size_t r = blockIdx.y; r < rows; r += gridDim.y)
+        dst[instance_major ? inst * rows + r : r * n_total + inst] = src[r * count + j];
+}
 #endif // !__CUDACC_EMU__
 
 #ifdef CLODE_WITH_FEATURES

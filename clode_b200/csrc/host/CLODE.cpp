@@ -6,6 +6,7 @@
 #include <cmath>
 #include <random>
 #include <stdexcept>
+#include <thread>
 
 namespace lg = clode_log;
 
@@ -192,37 +193,118 @@ void CLODE::setNpts(cl_int newNpts)
     lg::debug_("set nPts={}", nPts);
 }
 
-// host [rows][nPts] -> per-shard [rows][count]
-void CLODE::uploadRows(const std::vector<cl_double> &full, int rows, int (*setter)(clode_sim *, const double *, size_t),
-                       const char *where)
+// run fn on every non-empty shard, concurrently when there are several (one host thread per GPU: the staging copies
+// are CPU work, the DMAs go over separate PCIe links).  The runtime's error text is thread-local, so it travels back
+// with the status.
+void CLODE::forEachShard(const std::function<int(Shard &)> &fn, const char *where)
 {
-    if (shards().size() == 1) {
-        check(setter(shards()[0].sim, full.data(), full.size()), where);
+    std::vector<Shard *> busy;
+    for (auto &s : shards())
+        if (s.count) busy.push_back(&s);
+    if (busy.size() <= 1) {
+        for (Shard *s : busy) check(fn(*s), where);
         return;
     }
-    std::vector<double> part;
-    for (auto &s : shards()) {
-        if (s.count == 0) continue;
-        takeShard(full, (size_t)nPts, rows, s, part);
-        check(setter(s.sim, part.data(), part.size()), where);
+    std::vector<int> rc(busy.size(), CLODE_OK);
+    std::vector<std::string> msg(busy.size());
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < busy.size(); ++k)
+        workers.emplace_back([&, k] {
+            rc[k] = fn(*busy[k]);
+            if (rc[k]) msg[k] = clode_last_error();
+        });
+    for (auto &w : workers) w.join();
+    for (size_t k = 0; k < busy.size(); ++k)
+        if (rc[k]) {
+            lg::error_("{}:{}({})", where, msg[k], CLErrorString(rc[k]));
+            if (rc[k] == CLODE_ERR_MEMORY) throw std::invalid_argument(msg[k]);
+            throw std::runtime_error(std::string(where) + ": " + msg[k]);
+        }
+}
+
+// host [rows][nPts] -> per-shard [rows][count]
+void CLODE::uploadRows(const cl_double *full, int rows, int which, const char *where)
+{
+    const size_t pitch = (size_t)nPts;
+    forEachShard([&](Shard &s) { return clode_sim_set_rows(s.sim, which, full, (size_t)rows, pitch, s.first, s.stride); }, where);
+}
+
+// host element (row r, instance i) at a[r*rowStride + i*instStride] -> per-shard [rows][count]
+void CLODE::uploadMatrix(const cl_double *a, int rows, size_t rowStride, size_t instStride, int which, const char *where)
+{
+    forEachShard([&](Shard &s) {
+        return clode_sim_set_rows(s.sim, which, a, (size_t)rows, rowStride, s.first * instStride, s.stride * instStride);
+    }, where);
+}
+
+void CLODE::setX0Matrix(const cl_double *a, size_t rows, ptrdiff_t instStride, ptrdiff_t varStride)
+{
+    if (rows != (size_t)nPts || instStride <= 0 || varStride <= 0) {
+        lg::info_("...Initial conditions were not updated!");
+        return;
     }
+    if (nVar > 0 && nPts > 0) uploadMatrix(a, nVar, (size_t)varStride, (size_t)instStride, CLODE_BUF_X0, "CLODE::setX0");
+    lg::debug_("set X0");
+}
+
+void CLODE::setParsMatrix(const cl_double *a, size_t rows, ptrdiff_t instStride, ptrdiff_t parStride)
+{
+    if (rows != (size_t)nPts || instStride <= 0 || parStride <= 0) {
+        lg::info_("Invalid parameter vector: Expected {}*{} elements, recieved {}", nPts, nPar, rows * nPar);
+        lg::info_("...Parameters were not updated!");
+        return;
+    }
+    if (nPar > 0 && nPts > 0) uploadMatrix(a, nPar, (size_t)parStride, (size_t)instStride, CLODE_BUF_PARS, "CLODE::setPars");
+    parsOnDeviceOnly = true;
+    lg::debug_("set P");
+}
+
+void CLODE::setProblemDataMatrix(const cl_double *x0m, size_t nX0rows, ptrdiff_t x0InstStride, ptrdiff_t x0VarStride,
+                                 const cl_double *parsm, size_t nParsRows, ptrdiff_t parsInstStride, ptrdiff_t parsParStride)
+{
+    if (nPar > 0 && nX0rows != nParsRows) {
+        lg::info_("Initial contition and parameter vector dimensions don't match");
+        lg::info_("...Expected {} sets of each, recieved {} for x0 and {} for pars", nPts, nX0rows, nParsRows);
+        lg::info_("...Problem data was not updated!");
+        return;
+    }
+    setNpts((cl_int)nX0rows);
+    setX0Matrix(x0m, nX0rows, x0InstStride, x0VarStride);
+    setParsMatrix(parsm, nParsRows, parsInstStride, parsParStride);
+    lg::debug_("set problem data");
 }
 
 // per-shard [rows][count] -> host [rows][nPts]
+void CLODE::downloadRows(cl_double *full, int rows, int which, const char *where)
+{
+    if (shards().size() == 1) {
+        check(clode_sim_get_rows(shards()[0].sim, which, full, (size_t)rows, (size_t)nPts, 0, 1), where);
+        return;
+    }
+    // several GPUs: one NVLink gather to the first shard's GPU, one copy to the host (clode_gather_rows)
+    std::vector<clode_sim *> sims;
+    for (auto &s : shards()) sims.push_back(s.sim);
+    check(clode_gather_rows(sims.data(), (int)sims.size(), which, (size_t)rows, (size_t)nPts, full), where);
+}
+
 void CLODE::downloadRows(std::vector<cl_double> &full, int rows, int which, const char *where)
 {
     full.resize((size_t)rows * nPts);
-    if (shards().size() == 1) {
-        check(clode_sim_get(shards()[0].sim, which, full.data(), full.size()), where);
-        return;
-    }
-    std::vector<double> part;
-    for (auto &s : shards()) {
-        if (s.count == 0) continue;
-        part.resize((size_t)rows * s.count);
-        check(clode_sim_get(s.sim, which, part.data(), part.size()), where);
-        putShard(full, (size_t)nPts, rows, s, part);
-    }
+    downloadRows(full.data(), rows, which, where);
+}
+
+void CLODE::fetch(int which, int rows, cl_double *out, const char *where)
+{
+    if (nPts) downloadRows(out, rows, which, where);
+}
+
+// gathered (NVLink, when sharded) and transposed on the GPU, then one copy to the host
+void CLODE::fetchInstanceMajor(int which, int rows, cl_double *out, const char *where)
+{
+    if (!nPts) return;
+    std::vector<clode_sim *> sims;
+    for (auto &s : shards()) sims.push_back(s.sim);
+    check(clode_gather_rows_instance_major(sims.data(), (int)sims.size(), which, (size_t)rows, (size_t)nPts, out), where);
 }
 
 void CLODE::setProblemData(std::vector<cl_double> newX0, std::vector<cl_double> newPars)
@@ -253,9 +335,14 @@ void CLODE::setProblemData(std::vector<cl_double> newX0, std::vector<cl_double> 
 
 void CLODE::setX0(std::vector<cl_double> newX0)
 {
-    if (newX0.size() == (size_t)nPts * nVar) {
-        x0 = newX0;
-        uploadRows(x0, nVar, clode_sim_set_x0, "CLODE::setX0");
+    if (newX0.size() == (size_t)nPts * nVar) x0 = newX0;
+    setX0(newX0.data(), newX0.size());
+}
+
+void CLODE::setX0(const cl_double *newX0, size_t count)
+{
+    if (count == (size_t)nPts * nVar) {
+        if (nVar > 0 && nPts > 0) uploadRows(newX0, nVar, CLODE_BUF_X0, "CLODE::setX0");
         lg::debug_("set X0");
     } else {
         lg::info_("...Initial conditions were not updated!");
@@ -264,14 +351,60 @@ void CLODE::setX0(std::vector<cl_double> newX0)
 
 void CLODE::setPars(std::vector<cl_double> newPars)
 {
-    if (newPars.size() == (size_t)nPts * nPar) {
+    const bool ok = newPars.size() == (size_t)nPts * nPar;
+    setPars(newPars.data(), newPars.size());
+    if (ok) {
         pars = newPars;
-        uploadRows(pars, nPar, clode_sim_set_pars, "CLODE::setPars");
+        parsOnDeviceOnly = false;
+    }
+}
+
+void CLODE::setPars(const cl_double *newPars, size_t count)
+{
+    if (count == (size_t)nPts * nPar) {
+        if (nPar > 0 && nPts > 0) uploadRows(newPars, nPar, CLODE_BUF_PARS, "CLODE::setPars");
+        parsOnDeviceOnly = true; // the host mirror is refreshed on demand (getPars)
         lg::debug_("set P");
     } else {
-        lg::info_("Invalid parameter vector: Expected {}*{} elements, recieved {}", nPts, nPar, newPars.size());
+        lg::info_("Invalid parameter vector: Expected {}*{} elements, recieved {}", nPts, nPar, count);
         lg::info_("...Parameters were not updated!");
     }
+}
+
+const std::vector<cl_double> CLODE::getPars() const
+{
+    if (parsOnDeviceOnly && nPts && nPar) {
+        CLODE *self = const_cast<CLODE *>(this);
+        self->downloadRows(self->pars, nPar, CLODE_BUF_PARS, "CLODE::getPars");
+        parsOnDeviceOnly = false;
+    }
+    return pars;
+}
+
+void CLODE::setProblemData(const cl_double *newX0, size_t nX0, const cl_double *newPars, size_t nParsValues)
+{
+    if (nVar == 0 || nX0 % nVar != 0) {
+        lg::info_("Invalid initial condition vector: not a multiple of nVar={}", nVar);
+        lg::info_("...Initial conditions were not updated!");
+        return;
+    }
+    if (nPar > 0 && nParsValues % nPar != 0) {
+        lg::info_("Invalid parameter vector: not a multiple of nPar={}", nPar);
+        lg::info_("...Parameters were not updated!");
+        return;
+    }
+    cl_int nPtsX0 = (cl_int)(nX0 / nVar);
+    cl_int nPtsPars = nPar > 0 ? (cl_int)(nParsValues / nPar) : nPtsX0;
+    if (nPtsX0 != nPtsPars) {
+        lg::info_("Initial contition and parameter vector dimensions don't match");
+        lg::info_("...Expected {} sets of each, recieved {} for x0 and {} for pars", nPts, nPtsX0, nPtsPars);
+        lg::info_("...Problem data was not updated!");
+        return;
+    }
+    setNpts(nPtsX0);
+    setX0(newX0, nX0);
+    setPars(newPars, nParsValues);
+    lg::debug_("set problem data");
 }
 
 void CLODE::setTspan(std::vector<cl_double> newTspan)

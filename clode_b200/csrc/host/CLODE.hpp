@@ -8,6 +8,7 @@
 #include "clODE_struct_defs.hpp"
 #include "clode_rt.h"
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -101,9 +102,14 @@ protected:
     void buildProgram();
     void pushSolverParams();
     void setNpts(cl_int newNpts);
-    void uploadRows(const std::vector<cl_double> &full, int rows, int (*setter)(clode_sim *, const double *, size_t),
-                    const char *where);
+    // host [rows][nPts] <-> the shards: every shard moves its own columns (strided, through the runtime's page-locked
+    // staging ring), all shards concurrently; results of several GPUs come back through the NVLink gather
+    void uploadRows(const cl_double *full, int rows, int which, const char *where);
+    void uploadMatrix(const cl_double *a, int rows, size_t rowStride, size_t instStride, int which, const char *where);
+    void downloadRows(cl_double *full, int rows, int which, const char *where);
     void downloadRows(std::vector<cl_double> &full, int rows, int which, const char *where);
+    void forEachShard(const std::function<int(Shard &)> &fn, const char *where);
+    mutable bool parsOnDeviceOnly = false; // setPars(pointer) skipped the host mirror; getPars() fetches it on demand
     void runOnShards(int kernel, int initialize, const char *where);
     std::string getStepperDefine();
 
@@ -122,6 +128,19 @@ public:
     virtual void buildCL();
 
     void setProblemData(std::vector<cl_double> newX0, std::vector<cl_double> newPars);
+    // additions: the same calls on caller-owned memory (numpy buffers): no std::vector copy on the way in, results
+    // written straight into caller-owned (ideally page-locked, clode_host_alloc) memory on the way out
+    void setProblemData(const cl_double *newX0, size_t nX0, const cl_double *newPars, size_t nParsValues);
+    void setX0(const cl_double *newX0, size_t count);
+    void setPars(const cl_double *newPars, size_t count);
+    void fetch(int which, int rows, cl_double *out, const char *where = "CLODE::fetch"); // which = CLODE_BUF_*
+    void fetchInstanceMajor(int which, int rows, cl_double *out, const char *where = "CLODE::fetch"); // out[i*rows + r]
+    // (ensemble x nVar) / (ensemble x nPar) matrices with arbitrary element strides (numpy arrays as the Python front end
+    // holds them): transposed into the variable-major device layout inside the staging copy, no host-side flatten
+    void setProblemDataMatrix(const cl_double *x0, size_t nX0rows, ptrdiff_t x0InstStride, ptrdiff_t x0VarStride,
+                              const cl_double *pars, size_t nParsRows, ptrdiff_t parsInstStride, ptrdiff_t parsParStride);
+    void setX0Matrix(const cl_double *x0, size_t rows, ptrdiff_t instStride, ptrdiff_t varStride);
+    void setParsMatrix(const cl_double *pars, size_t rows, ptrdiff_t instStride, ptrdiff_t parStride);
     void setTspan(std::vector<cl_double> newTspan);
     void setX0(std::vector<cl_double> newX0);
     void setPars(std::vector<cl_double> newPars);
@@ -138,7 +157,7 @@ public:
     const ProblemInfo getProblemInfo() const { return prob; }
     const std::vector<cl_double> getTspan() const { return tspan; }
     const SolverParams<cl_double> getSolverParams() const { return sp; }
-    const std::vector<cl_double> getPars() const { return pars; }
+    const std::vector<cl_double> getPars() const;
     const std::vector<cl_double> getX0();
     const std::vector<cl_double> getXf();
     const std::vector<cl_double> getDt();
@@ -148,6 +167,9 @@ public:
     const std::string getProgramString() const { return buildOptions + clprogramstring + ODEsystemsource; }
     void printStatus();
 
+    int getNpts() const { return nPts; }
+    int getNvar() const { return nVar; }
+    int getNpar() const { return nPar; }
     // additions (not in the reference): measurement hooks used by bench/tests
     double getLastKernelMilliseconds() const;
     std::vector<unsigned int> getStepCounts();

@@ -10,6 +10,10 @@
 #include "CLODEtrajectory.hpp"
 #include "clode_log.hpp"
 
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 namespace py = pybind11;
 using dvec = std::vector<double>;
 using darray = py::array_t<double, py::array::c_style | py::array::forcecast>;
@@ -21,13 +25,80 @@ static std::string vector_to_string(const std::vector<std::string> &vec)
     return out + "]";
 }
 
-static dvec to_vec(const darray &a) { return dvec(a.data(), a.data() + a.size()); }
 static py::array_t<double> to_array(const dvec &v)
 {
     py::array_t<double> a((py::ssize_t)v.size());
     std::copy(v.begin(), v.end(), a.mutable_data());
     return a;
 }
+
+// Result arrays handed to numpy are backed by PAGE-LOCKED memory from the runtime (clode_host_alloc), so the
+// device-to-host copy that fills them runs at the full PCIe rate and lands in the array the user gets — no std::vector
+// in between (the reference: device -> std::vector -> Python list -> np.array, clode/features.py:516-524).  Pinning
+// pages is slow (~0.3 ms/MB), so blocks go back to a small pool when numpy drops the array and are reused by size.
+namespace {
+struct PinnedPool {
+    std::mutex m;
+    std::multimap<size_t, void *> idle;
+    size_t idle_bytes = 0;
+    static constexpr size_t kMaxIdle = size_t(4) << 30;
+    struct Block { void *p; size_t bytes; bool pinned; };
+
+    Block take(size_t bytes)
+    {
+        bytes = std::max<size_t>((bytes + 4095) & ~size_t(4095), 4096);
+        {
+            std::lock_guard<std::mutex> lock(m);
+            auto it = idle.find(bytes);
+            if (it != idle.end()) {
+                void *p = it->second;
+                idle.erase(it);
+                idle_bytes -= bytes;
+                return {p, bytes, true};
+            }
+        }
+        if (void *p = clode_host_alloc(0, bytes)) return {p, bytes, true};
+        return {std::malloc(bytes), bytes, false}; // no driver (CPU-only import) or out of lockable memory: pageable
+    }
+    void give(Block b)
+    {
+        if (!b.pinned) { std::free(b.p); return; }
+        std::lock_guard<std::mutex> lock(m);
+        if (idle_bytes + b.bytes > kMaxIdle) { clode_host_free(b.p); return; }
+        idle.emplace(b.bytes, b.p);
+        idle_bytes += b.bytes;
+    }
+    static PinnedPool &get() { static PinnedPool *pool = new PinnedPool(); return *pool; } // leaked on purpose: outlives numpy arrays at exit
+};
+
+// a flat float64 array of `count` elements on a pooled page-locked block, filled by `fill(double *)`
+template <class Fill> py::array_t<double> pinned_array(size_t count, Fill &&fill)
+{
+    PinnedPool::Block b = PinnedPool::get().take(std::max<size_t>(count, 1) * sizeof(double));
+    if (!b.p) throw std::bad_alloc();
+    try {
+        py::gil_scoped_release release;
+        fill(static_cast<double *>(b.p));
+    } catch (...) {
+        PinnedPool::get().give(b);
+        throw;
+    }
+    auto *owner = new PinnedPool::Block(b);
+    py::capsule keep(owner, [](void *o) {
+        auto *blk = static_cast<PinnedPool::Block *>(o);
+        PinnedPool::get().give(*blk);
+        delete blk;
+    });
+    return py::array_t<double>({(py::ssize_t)count}, {(py::ssize_t)sizeof(double)}, static_cast<double *>(b.p), keep);
+}
+
+// (ensemble, cols) C-contiguous matrix, transposed on the GPU
+template <class Fill> py::array_t<double> pinned_matrix(size_t n, size_t cols, Fill &&fill)
+{
+    py::array_t<double> flat = pinned_array(n * cols, fill);
+    return flat.reshape({(py::ssize_t)n, (py::ssize_t)cols});
+}
+} // namespace
 
 struct LoggerSingleton {
     LoggerSingleton()
@@ -186,13 +257,37 @@ PYBIND11_MODULE(clode_cpp_wrapper, m)
         .def("set_opencl", static_cast<void (CLODE::*)(unsigned int, unsigned int)>(&CLODE::setOpenCL))
         .def("build_cl", &CLODE::buildCL)
         // ndarray fast paths first (one memcpy instead of a per-element list conversion), then the reference's list forms
-        .def("set_problem_data", [](CLODE &c, const darray &x0, const darray &p) { c.setProblemData(to_vec(x0), to_vec(p)); })
-        .def("set_problem_data", &CLODE::setProblemData)
+        .def("set_problem_data", [](CLODE &c, const darray &x0, const darray &p) {
+            const double *px = x0.data(), *pp = p.data();
+            const size_t nx = (size_t)x0.size(), np_ = (size_t)p.size();
+            py::gil_scoped_release release;
+            c.setProblemData(px, nx, pp, np_);
+        })
+        .def("set_problem_data", static_cast<void (CLODE::*)(dvec, dvec)>(&CLODE::setProblemData))
+        // additions: (ensemble, nVar) / (ensemble, nPar) float64 matrices with any positive strides, uploaded as they are
+        .def("set_problem_data_matrix", [](CLODE &c, const py::array_t<double> &x0, const py::array_t<double> &p) {
+            if (x0.ndim() != 2 || p.ndim() != 2) throw std::invalid_argument("set_problem_data_matrix: 2-D arrays expected");
+            if (x0.shape(1) != c.getNvar() || p.shape(1) != c.getNpar()) throw std::invalid_argument("set_problem_data_matrix: wrong number of columns");
+            const double *px = x0.data(), *pp = p.data();
+            const size_t nx = (size_t)x0.shape(0), np_ = (size_t)p.shape(0);
+            const ptrdiff_t xi = x0.strides(0) / 8, xv = x0.shape(1) > 1 ? x0.strides(1) / 8 : 1;
+            const ptrdiff_t pi = p.strides(0) / 8, pv = p.shape(1) > 1 ? p.strides(1) / 8 : 1;
+            py::gil_scoped_release release;
+            c.setProblemDataMatrix(px, nx, nx > 1 ? xi : 1, xv, pp, np_, np_ > 1 ? pi : 1, pv);
+        })
+        .def("set_x0_matrix", [](CLODE &c, const py::array_t<double> &x0) {
+            if (x0.ndim() != 2 || x0.shape(1) != c.getNvar()) throw std::invalid_argument("set_x0_matrix: (ensemble, nVar) array expected");
+            c.setX0Matrix(x0.data(), (size_t)x0.shape(0), x0.shape(0) > 1 ? x0.strides(0) / 8 : 1, x0.shape(1) > 1 ? x0.strides(1) / 8 : 1);
+        })
+        .def("set_pars_matrix", [](CLODE &c, const py::array_t<double> &p) {
+            if (p.ndim() != 2 || p.shape(1) != c.getNpar()) throw std::invalid_argument("set_pars_matrix: (ensemble, nPar) array expected");
+            c.setParsMatrix(p.data(), (size_t)p.shape(0), p.shape(0) > 1 ? p.strides(0) / 8 : 1, p.shape(1) > 1 ? p.strides(1) / 8 : 1);
+        })
         .def("set_tspan", &CLODE::setTspan)
-        .def("set_x0", [](CLODE &c, const darray &x0) { c.setX0(to_vec(x0)); })
-        .def("set_x0", &CLODE::setX0)
-        .def("set_pars", [](CLODE &c, const darray &p) { c.setPars(to_vec(p)); })
-        .def("set_pars", &CLODE::setPars)
+        .def("set_x0", [](CLODE &c, const darray &x0) { c.setX0(x0.data(), (size_t)x0.size()); })
+        .def("set_x0", static_cast<void (CLODE::*)(dvec)>(&CLODE::setX0))
+        .def("set_pars", [](CLODE &c, const darray &p) { c.setPars(p.data(), (size_t)p.size()); })
+        .def("set_pars", static_cast<void (CLODE::*)(dvec)>(&CLODE::setPars))
         .def("set_solver_params", &CLODE::setSolverParams)
         .def("seed_rng", static_cast<void (CLODE::*)()>(&CLODE::seedRNG), "Seed RNG")
         .def("seed_rng", static_cast<void (CLODE::*)(int)>(&CLODE::seedRNG), "Seed RNG", py::arg("seed"))
@@ -211,10 +306,13 @@ PYBIND11_MODULE(clode_cpp_wrapper, m)
         .def("get_program_string", &CLODE::getProgramString)
         .def("print_status", &CLODE::printStatus)
         // additions
-        .def("get_x0_array", [](CLODE &c) { return to_array(c.getX0()); })
-        .def("get_xf_array", [](CLODE &c) { return to_array(c.getXf()); })
-        .def("get_dt_array", [](CLODE &c) { return to_array(c.getDt()); })
-        .def("get_tf_array", [](CLODE &c) { return to_array(c.getTf()); })
+        .def("get_x0_array", [](CLODE &c) { return pinned_array((size_t)c.getNvar() * c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_X0, c.getNvar(), o, "CLODE::getX0"); }); })
+        .def("get_xf_array", [](CLODE &c) { return pinned_array((size_t)c.getNvar() * c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_XF, c.getNvar(), o, "CLODE::getXf"); }); })
+        .def("get_dt_array", [](CLODE &c) { return pinned_array((size_t)c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_DT, 1, o, "CLODE::getDt"); }); })
+        .def("get_tf_array", [](CLODE &c) { return pinned_array((size_t)c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_TF, 1, o, "CLODE::getTf"); }); })
+        .def("get_xf_matrix", [](CLODE &c) { return pinned_matrix((size_t)c.getNpts(), (size_t)c.getNvar(), [&](double *o) { c.fetchInstanceMajor(CLODE_BUF_XF, c.getNvar(), o, "CLODE::getXf"); }); })
+        .def("get_x0_matrix", [](CLODE &c) { return pinned_matrix((size_t)c.getNpts(), (size_t)c.getNvar(), [&](double *o) { c.fetchInstanceMajor(CLODE_BUF_X0, c.getNvar(), o, "CLODE::getX0"); }); })
+        .def("get_pars_array", [](CLODE &c) { return pinned_array((size_t)c.getNpar() * c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_PARS, c.getNpar(), o, "CLODE::getPars"); }); })
         .def("get_step_counts", [](CLODE &c) {
             auto v = c.getStepCounts();
             py::array_t<unsigned int> a((py::ssize_t)v.size());
@@ -272,7 +370,8 @@ PYBIND11_MODULE(clode_cpp_wrapper, m)
         .def("get_observer_params", &CLODEfeatures::getObserverParams)
         .def("get_observer_name", &CLODEfeatures::getObserverName)
         .def("get_f", &CLODEfeatures::getF)
-        .def("get_f_array", [](CLODEfeatures &c) { return to_array(c.getF()); })
+        .def("get_f_array", [](CLODEfeatures &c) { return pinned_array((size_t)c.getNFeatures() * c.getNpts(), [&](double *o) { c.fetch(CLODE_BUF_F, c.getNFeatures(), o, "CLODEfeatures::getF"); }); })
+        .def("get_f_matrix", [](CLODEfeatures &c) { return pinned_matrix((size_t)c.getNpts(), (size_t)c.getNFeatures(), [&](double *o) { c.fetchInstanceMajor(CLODE_BUF_F, c.getNFeatures(), o, "CLODEfeatures::getF"); }); })
         .def("get_n_features", &CLODEfeatures::getNFeatures)
         .def("get_feature_names", &CLODEfeatures::getFeatureNames)
         .def("get_available_observers", &CLODEfeatures::getAvailableObservers)

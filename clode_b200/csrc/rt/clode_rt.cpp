@@ -449,7 +449,12 @@ struct clode_sim {
     Buffer cost; // 2 x 2 u64: accepted steps in the lower / upper half of the ensemble (block_order auto)
     // cost-sorted chunked execution of the adaptive time loops (kernels.cuh "Scheduling")
     Buffer park_real, park_uint, perm[2], sched_bucket, sched_hist, sched_cursor, sched_state;
-    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr;
+    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr, k_interleave = nullptr;
+    // page-locked staging ring for strided / converting host transfers (clode_sim_set_rows / get_rows)
+    static constexpr size_t kStageBytes = 4u << 20;
+    void *stage[2] = {nullptr, nullptr};
+    CUevent stage_done[2] = {nullptr, nullptr};
+    Buffer gather_tmp, gathered; // NVLink gather on the root shard (clode_gather_rows)
     int perm_cur = 0;
     bool warmup_costs_fresh = false; // park_uint holds the step counts of a warm-up pass over the current problem
     size_t tr_rows = 0; // allocated trajectory rows (max_store + 1)
@@ -535,10 +540,91 @@ struct clode_sim {
         return CLODE_OK;
     }
 
+    int ensure_stage()
+    {
+        for (int k = 0; k < 2; ++k) {
+            if (!stage[k]) {
+                int rc = cu(d->cuMemHostAlloc(&stage[k], kStageBytes, 0), "staging ring");
+                if (rc) return rc;
+            }
+            if (!stage_done[k]) {
+                int rc = cu(d->cuEventCreate(&stage_done[k], CU_EVENT_DISABLE_TIMING), "staging ring");
+                if (rc) return rc;
+            }
+        }
+        return CLODE_OK;
+    }
+
+    // host [rows][pitch], columns first + k*stride  <->  device [rows][n] realtype, through the staging ring
+    template <class T> int staged_rows(bool to_device, CUdeviceptr dev, double *host, size_t rows, size_t pitch, size_t first,
+                                       size_t stride, const char *what)
+    {
+        int rc = ensure_stage();
+        if (rc) return rc;
+        const size_t chunk = kStageBytes / sizeof(T);
+        int slot = 0;
+        bool used[2] = {false, false};
+        // device -> host: the scatter of a chunk runs one step behind its copy, so the next copy is already on the wire
+        struct Pending { bool on = false; size_t row = 0, e0 = 0, cnt = 0; } prev[2];
+        auto scatter = [&](int k) {
+            if (!prev[k].on) return;
+            d->cuEventSynchronize(stage_done[k]);
+            const T *src = (const T *)stage[k];
+            double *dst = host + prev[k].row * pitch + first + prev[k].e0 * stride;
+            for (size_t j = 0; j < prev[k].cnt; ++j) dst[j * stride] = (double)src[j];
+            prev[k].on = false;
+        };
+        for (size_t r = 0; r < rows; ++r) {
+            for (size_t e0 = 0; e0 < n; e0 += chunk) {
+                const size_t cnt = std::min(chunk, n - e0);
+                const CUdeviceptr dptr = dev + (r * n + e0) * sizeof(T);
+                if (to_device) {
+                    if (used[slot] && (rc = cu(d->cuEventSynchronize(stage_done[slot]), what))) return rc;
+                    T *dst = (T *)stage[slot];
+                    const double *src = host + r * pitch + first + e0 * stride;
+                    for (size_t j = 0; j < cnt; ++j) dst[j] = (T)src[j * stride];
+                    if ((rc = cu(d->cuMemcpyHtoDAsync(dptr, dst, cnt * sizeof(T), stream), what))) return rc;
+                } else {
+                    scatter(slot); // the data this slot held two chunks ago
+                    if ((rc = cu(d->cuMemcpyDtoHAsync(stage[slot], dptr, cnt * sizeof(T), stream), what))) return rc;
+                    prev[slot].on = true; prev[slot].row = r; prev[slot].e0 = e0; prev[slot].cnt = cnt;
+                }
+                if ((rc = cu(d->cuEventRecord(stage_done[slot], stream), what))) return rc;
+                used[slot] = true;
+                slot ^= 1;
+            }
+        }
+        if (!to_device) { scatter(slot); scatter(slot ^ 1); }
+        return cu(d->cuStreamSynchronize(stream), what);
+    }
+
+    int transfer_rows(bool to_device, Buffer &b, double *host, size_t rows, size_t pitch, size_t first, size_t stride, const char *what)
+    {
+        if (rows * n * real_size > b.bytes || !b.ptr) return fail(CLODE_ERR_INVALID, std::string(what) + ": size mismatch");
+        if (n == 0 || rows == 0) return CLODE_OK;
+        if (stride == 0) return fail(CLODE_ERR_INVALID, std::string(what) + ": stride must be positive");
+        if (real_size == 8 && stride == 1) { // contiguous rows of doubles: straight DMA, no staging
+            int rc = CLODE_OK;
+            if (pitch == n) {
+                rc = to_device ? cu(d->cuMemcpyHtoDAsync(b.ptr, host, rows * n * 8, stream), what)
+                               : cu(d->cuMemcpyDtoHAsync(host, b.ptr, rows * n * 8, stream), what);
+            } else {
+                for (size_t r = 0; r < rows && !rc; ++r)
+                    rc = to_device ? cu(d->cuMemcpyHtoDAsync(b.ptr + r * n * 8, host + r * pitch + first, n * 8, stream), what)
+                                   : cu(d->cuMemcpyDtoHAsync(host + r * pitch + first, b.ptr + r * n * 8, n * 8, stream), what);
+            }
+            if (rc) return rc;
+            return cu(d->cuStreamSynchronize(stream), what);
+        }
+        return real_size == 8 ? staged_rows<double>(to_device, b.ptr, host, rows, pitch, first, stride, what)
+                              : staged_rows<float>(to_device, b.ptr, host, rows, pitch, first, stride, what);
+    }
+
     void free_ensemble()
     {
         Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue, &cost,
                          &park_real, &park_uint, &perm[0], &perm[1], &sched_bucket, &sched_hist, &sched_cursor, &sched_state,
+                         &gather_tmp, &gathered,
                          &chunk[0].t, &chunk[0].x, &chunk[0].dx, &chunk[0].aux, &chunk[1].t, &chunk[1].x, &chunk[1].dx, &chunk[1].aux,
                          &rs_real, &rs_uint, &chunk_flags};
         for (Buffer *b : all) release(*b);
@@ -955,6 +1041,10 @@ int clode_sim_destroy(clode_sim *s)
         s->free_ensemble();
         if (s->module) s->d->cuModuleUnload(s->module);
         if (s->flags_host) s->d->cuMemFreeHost(s->flags_host);
+        for (int k = 0; k < 2; ++k) {
+            if (s->stage[k]) s->d->cuMemFreeHost(s->stage[k]);
+            if (s->stage_done[k]) s->d->cuEventDestroy(s->stage_done[k]);
+        }
         if (s->ev0) s->d->cuEventDestroy(s->ev0);
         if (s->ev1) s->d->cuEventDestroy(s->ev1);
         if (s->stream) s->d->cuStreamDestroy(s->stream);
@@ -993,6 +1083,7 @@ static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_hist, s->module, "clode_sched_histogram"), "clode_sched_histogram"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scan, s->module, "clode_sched_scan"), "clode_sched_scan"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scatter, s->module, "clode_sched_scatter"), "clode_sched_scatter"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_interleave, s->module, "clode_interleave_rows"), "clode_interleave_rows"))) return rc;
     // per-thread local memory (spills + stack) of each time-loop kernel; -1 = kernel not in this program
     CUfunction loops[4] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory};
     for (int k = 0; k < 4; ++k) {
@@ -1528,6 +1619,126 @@ static Buffer *pick_buffer(clode_sim *s, int which, int *elem)
     }
     if (elem) *elem = e;
     return b;
+}
+
+int clode_sim_set_rows(clode_sim *s, int which, const double *host, size_t rows, size_t host_pitch, size_t first, size_t stride)
+{
+    if (!s || !host) return fail(CLODE_ERR_INVALID, "null argument");
+    if (which != CLODE_BUF_X0 && which != CLODE_BUF_PARS && which != CLODE_BUF_DT)
+        return fail(CLODE_ERR_INVALID, "set_rows: only x0, pars and dt can be written");
+    Buffer *b = pick_buffer(s, which, nullptr);
+    clode_sim::Scope scope(s);
+    return s->transfer_rows(true, *b, const_cast<double *>(host), rows, host_pitch, first, stride, "set_rows");
+}
+
+int clode_sim_get_rows(clode_sim *s, int which, double *host, size_t rows, size_t host_pitch, size_t first, size_t stride)
+{
+    if (!s || !host) return fail(CLODE_ERR_INVALID, "null argument");
+    if (which < CLODE_BUF_X0 || which > CLODE_BUF_AUX) return fail(CLODE_ERR_INVALID, "get_rows: not a real-valued buffer");
+    Buffer *b = pick_buffer(s, which, nullptr);
+    if (!b->ptr) return fail(CLODE_ERR_STATE, "get_rows: buffer not allocated yet (run the simulation first)");
+    clode_sim::Scope scope(s);
+    int rc = s->wait("get_rows");
+    if (rc) return rc;
+    return s->transfer_rows(false, *b, host, rows, host_pitch, first, stride, "get_rows");
+}
+
+static int gather_rows_impl(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host, unsigned instance_major);
+int clode_gather_rows(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host)
+{
+    return gather_rows_impl(shards, n_shards, which, rows, n_total, host, 0u);
+}
+int clode_gather_rows_instance_major(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host)
+{
+    return gather_rows_impl(shards, n_shards, which, rows, n_total, host, 1u);
+}
+static int gather_rows_impl(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host, unsigned instance_major)
+{
+    if (!shards || n_shards < 1 || !shards[0]) return fail(CLODE_ERR_INVALID, "gather_rows: no shards");
+    if (which < CLODE_BUF_X0 || which > CLODE_BUF_AUX) return fail(CLODE_ERR_INVALID, "gather_rows: not a real-valued buffer");
+    clode_sim *root = shards[0];
+    DriverApi *d = root->d;
+    const size_t rs = root->real_size, G = (size_t)n_shards;
+    size_t total = 0;
+    for (int g = 0; g < n_shards; ++g) {
+        if (!shards[g] || shards[g]->real_size != rs) return fail(CLODE_ERR_INVALID, "gather_rows: shards of different precision");
+        const size_t want = n_total > (size_t)g ? (n_total - g + G - 1) / G : 0;
+        if (shards[g]->n != want) return fail(CLODE_ERR_INVALID, "gather_rows: shard sizes do not form an interleaved partition of n_total");
+        total += shards[g]->n;
+    }
+    if (total != n_total) return fail(CLODE_ERR_INVALID, "gather_rows: shard sizes do not add up to n_total");
+    if (n_total == 0 || rows == 0) return CLODE_OK;
+    int rc;
+    {
+        clode_sim::Scope scope(root);
+        if ((rc = root->alloc(root->gathered, rs * rows * n_total, "gathered rows"))) return rc;
+        if ((rc = root->alloc(root->gather_tmp, rs * rows * (n_total - root->n) + 8, "gather staging"))) return rc;
+        if (!root->k_interleave) return fail(CLODE_ERR_STATE, "gather_rows: program not built");
+    }
+    size_t tmp_off = 0;
+    for (int g = 0; g < n_shards; ++g) {
+        clode_sim *s = shards[g];
+        if (s->n == 0) continue;
+        Buffer *b = pick_buffer(s, which, nullptr);
+        if (!b->ptr || b->bytes < rs * rows * s->n) return fail(CLODE_ERR_STATE, "gather_rows: shard buffer missing or too small");
+        CUdeviceptr src = b->ptr;
+        if (g > 0) {
+            // order the copy behind the shard's pending kernels without a host synchronisation
+            CUevent ready = nullptr;
+            {
+                clode_sim::Scope scope(s);
+                if (!s->stage_done[0] && (rc = s->ensure_stage())) return rc;
+                ready = s->stage_done[0];
+                if ((rc = s->cu(d->cuEventRecord(ready, s->stream), "gather_rows: event"))) return rc;
+            }
+            clode_sim::Scope scope(root);
+            if (s->device != root->device) {
+                CUresult pr = d->cuCtxEnablePeerAccess(s->ctx, 0); // direct NVLink path; "already enabled" is fine
+                if (pr != CUDA_SUCCESS && pr != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED && pr != CUDA_ERROR_PEER_ACCESS_UNSUPPORTED)
+                    return root->cu(pr, "cuCtxEnablePeerAccess");
+            }
+            if ((rc = root->cu(d->cuStreamWaitEvent(root->stream, ready, 0), "gather_rows: wait"))) return rc;
+            const CUdeviceptr dst = root->gather_tmp.ptr + tmp_off;
+            const size_t bytes = rs * rows * s->n;
+            if ((rc = root->cu(d->cuMemcpyPeerAsync(dst, root->ctx, src, s->ctx, bytes, root->stream), "cuMemcpyPeerAsync"))) return rc;
+            src = dst;
+            tmp_off += bytes;
+        }
+        clode_sim::Scope scope(root);
+        unsigned long long rows_ = rows, count = s->n, nt = n_total, first = (unsigned long long)g, stride = G;
+        unsigned im = instance_major;
+        void *params[] = {&root->gathered.ptr, &src, &rows_, &count, &nt, &first, &stride, &im};
+        const unsigned gx = (unsigned)((s->n + 255) / 256), gy = (unsigned)std::min<size_t>(rows, 64);
+        if ((rc = root->cu(d->cuLaunchKernel(root->k_interleave, gx, gy, 1, 256, 1, 1, 0, root->stream, params, nullptr), "clode_interleave_rows"))) return rc;
+        ++root->launches;
+    }
+    {
+        clode_sim::Scope scope(root);
+        if (host) {
+            if (rs == 8) {
+                if ((rc = root->cu(d->cuMemcpyDtoHAsync(host, root->gathered.ptr, 8 * rows * n_total, root->stream), "gather_rows: copy to host"))) return rc;
+            } else {
+                std::vector<float> narrow(rows * n_total);
+                if ((rc = root->cu(d->cuMemcpyDtoHAsync(narrow.data(), root->gathered.ptr, 4 * rows * n_total, root->stream), "gather_rows: copy to host"))) return rc;
+                if ((rc = root->cu(d->cuStreamSynchronize(root->stream), "gather_rows"))) return rc;
+                for (size_t k = 0; k < rows * n_total; ++k) host[k] = (double)narrow[k];
+            }
+        }
+        if ((rc = root->cu(d->cuStreamSynchronize(root->stream), "gather_rows"))) return rc;
+    }
+    for (int g = 0; g < n_shards; ++g) { // the shards' kernels are complete now: close their timing
+        clode_sim::Scope scope(shards[g]);
+        if ((rc = shards[g]->wait("gather_rows"))) return rc;
+    }
+    return CLODE_OK;
+}
+
+int clode_gathered_device_ptr(clode_sim *root, uint64_t *device_ptr, size_t *bytes)
+{
+    if (!root || !device_ptr) return fail(CLODE_ERR_INVALID, "null argument");
+    *device_ptr = (uint64_t)root->gathered.ptr;
+    if (bytes) *bytes = root->gathered.bytes;
+    return CLODE_OK;
 }
 
 int clode_sim_get(clode_sim *s, int which, double *out, size_t count)

@@ -27,7 +27,8 @@ namespace clode {
     X(cuCtxPushCurrent) X(cuCtxPopCurrent)                                                        \
     X(cuMemAlloc) X(cuMemFree) X(cuMemcpyHtoD) X(cuMemcpyDtoH) X(cuMemcpyDtoDAsync)               \
     X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemsetD8Async) X(cuMemsetD32Async)              \
-    X(cuMemHostAlloc) X(cuMemFreeHost)                                                            \
+    X(cuMemHostAlloc) X(cuMemFreeHost) X(cuPointerGetAttribute) X(cuMemcpyPeerAsync)              \
+    X(cuCtxEnablePeerAccess) X(cuDeviceCanAccessPeer) X(cuStreamWaitEvent)                        \
     X(cuStreamCreate) X(cuStreamDestroy) X(cuStreamSynchronize)                                   \
     X(cuEventCreate) X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) \
     X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuModuleGetGlobal)                                  \

@@ -33,7 +33,13 @@ class ObserverOutput:
         self._feature_names = feature_names
         self._ensemble_shape = ensemble_shape
         dtype = np.dtype({"names": feature_names, "formats": [np.float64] * len(feature_names)})
-        self.F = rfn.unstructured_to_structured(feature_array, dtype=dtype)
+        a = np.asarray(feature_array)
+        if a.ndim == 2 and a.dtype == np.float64 and a.flags.c_contiguous and a.shape[1] == len(feature_names):
+            # (ensemble, features) matrix as the native layer delivers it (transposed on the GPU): the record array is
+            # a VIEW of it — the reference's unstructured_to_structured copy (clode/features.py:51) costs ~100 ms at 2^20
+            self.F = a.view(dtype).reshape(a.shape[0])
+        else:
+            self.F = rfn.unstructured_to_structured(a, dtype=dtype)
 
     def __repr__(self) -> str:
         return (f"ObserverOutput( ensemble size: {len(self.F[self._feature_names[0]])}, number of features: "
@@ -215,6 +221,9 @@ class FeatureSimulator(Simulator):
     def get_observer_results(self) -> ObserverOutput:
         if self._device_features is None:
             self._num_features = self._integrator.get_n_features()
-            self._device_features = self._matrix(self._integrator.get_f_array(), self._num_features)
+            if hasattr(self._integrator, "get_f_matrix"):
+                self._device_features = self._integrator.get_f_matrix()
+            else:
+                self._device_features = self._matrix(self._integrator.get_f_array(), self._num_features)
         return ObserverOutput(self._op, self._device_features, self._num_features, self.variable_names,
                               self._observer_type, self._integrator.get_feature_names(), self._ensemble_shape)

@@ -188,6 +188,34 @@ CLODE_API int clode_sim_get_n_stored(clode_sim *sim, int *out, size_t count);   
 CLODE_API int clode_sim_get_steps(clode_sim *sim, uint32_t *out, size_t count);      /* accepted steps of the last call */
 CLODE_API int clode_sim_n_features(clode_sim *sim, int *n_features);
 
+/* Strided host access, for callers that keep ONE host array for an ensemble spread over several GPUs (the reference's
+ * unused multi-device hook, OpenCLResource.hpp:104): the simulation object holds the instances first, first+stride, ...
+ * of a global ensemble whose host arrays are [rows][host_pitch].  set_rows gathers that column set from `host` into the
+ * device buffer `which` ([rows][nPts] on the device), get_rows scatters the device buffer back.  Both go through a
+ * page-locked staging ring inside the runtime: the gather / scatter (and the float<->double conversion of single-
+ * precision programs) happens in the same pass that fills the ring, while the previous chunk is on the wire.
+ * first = 0, stride = 1, host_pitch = nPts is the plain whole-array transfer (CLODE::setX0, CLODE::getXf, ...).
+ * Element (row r, local column k) lives at host[r*host_pitch + first + k*stride]; nothing else is assumed, so an
+ * instance-major matrix a[i*nVar + j] (the Python front end's (ensemble, nVar) arrays) is passed as host_pitch = 1,
+ * stride = nVar and transposed into the variable-major device layout by the same staging pass. */
+CLODE_API int clode_sim_set_rows(clode_sim *sim, int which, const double *host, size_t rows, size_t host_pitch,
+                                 size_t first, size_t stride);
+CLODE_API int clode_sim_get_rows(clode_sim *sim, int which, double *host, size_t rows, size_t host_pitch,
+                                 size_t first, size_t stride);
+
+/* The path's one exchange step (north_star: "only a final NVLink gather of features and final states"): the buffers
+ * `which` of `n_shards` simulation objects — shard g holding instances g, g+n_shards, ... of a global ensemble of
+ * n_total — are copied device-to-device over NVLink to `shards[0]`'s GPU (cuMemcpyPeerAsync, ordered behind each shard's
+ * pending kernels by events, no host synchronisation in between), interleaved there into the global [rows][n_total]
+ * layout by a small kernel, and brought to `host` with ONE device-to-host copy (full PCIe rate when `host` comes from
+ * clode_host_alloc).  host may be NULL: the gathered array then stays on shards[0]'s GPU (clode_gathered_device_ptr). */
+CLODE_API int clode_gather_rows(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host);
+/* the same with the result transposed on the GPU to instance-major host[i*rows + r] — the layout of the Python front
+ * end's record arrays (ObserverOutput.F, clode/features.py:51): one coalesced-read kernel instead of a host-side
+ * unstructured_to_structured pass.  n_shards may be 1. */
+CLODE_API int clode_gather_rows_instance_major(clode_sim *const *shards, int n_shards, int which, size_t rows, size_t n_total, double *host);
+CLODE_API int clode_gathered_device_ptr(clode_sim *root, uint64_t *device_ptr, size_t *bytes);
+
 /* raw device access for zero-copy consumers (e.g. wrap as a torch tensor for an NCCL gather):
  * pointer, size in bytes, element size (4 or 8) */
 CLODE_API int clode_sim_device_buffer(clode_sim *sim, int which, uint64_t *device_ptr, size_t *bytes, int *elem_size);
