@@ -218,17 +218,20 @@ class Simulator:
     def _make_problem_data(self, variables=None, parameters=None, new_size=None, new_shape=None):
         if len(new_shape) == 1:
             new_shape = (new_size, 1)
-        # keep the current state when the ensemble keeps its size or grows from a single instance
-        if self._ensemble_size in (new_size, 1):
-            x0 = np.array(self.get_initial_state(), dtype=np.float64)
-            p = np.array(self._device_parameters, dtype=np.float64)
-        else:
-            x0 = np.array(list(self._variable_defaults.values()), dtype=np.float64, ndmin=2)
-            p = np.array(list(self._parameter_defaults.values()), dtype=np.float64, ndmin=2)
-        if x0.shape[0] == 1:
-            x0 = np.tile(x0, (new_size, 1))
-        if p.shape[0] == 1:
-            p = np.tile(p, (new_size, 1))
+        # keep the current state when the ensemble keeps its size or grows from a single instance; a side that is given
+        # as a complete matrix needs no starting point at all (and no read-back of the device's current state)
+        keep = self._ensemble_size in (new_size, 1)
+        x0 = p = None
+        if not isinstance(variables, np.ndarray):
+            x0 = (np.array(self.get_initial_state(), dtype=np.float64) if keep else
+                  np.array(list(self._variable_defaults.values()), dtype=np.float64, ndmin=2))
+            if x0.shape[0] == 1:
+                x0 = np.tile(x0, (new_size, 1))
+        if not isinstance(parameters, np.ndarray):
+            p = (np.array(self._device_parameters, dtype=np.float64) if keep else
+                 np.array(list(self._parameter_defaults.values()), dtype=np.float64, ndmin=2))
+            if p.shape[0] == 1:
+                p = np.tile(p, (new_size, 1))
         for spec, target, names in ((variables, "x0", self.variable_names), (parameters, "p", self.parameter_names)):
             if isinstance(spec, np.ndarray):
                 if target == "x0":

@@ -14,7 +14,7 @@ out=gpurun_out/${tag}_sweep.log
 run() { # label, "ENV=VALUE ...", bench arguments...
   label=$1; envs=$2; shift 2
   line=$(env $envs python bench.py --steps 5 --warmup 3 --no-cpu-baseline "$@" 2>"gpurun_out/${tag}_err.log" | tail -1)
-  echo "$label | $(echo "$line" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); k=d["config"].get("kernel",{}); print(d["ms_per_step"], d["value"], k.get("registers"), k.get("local_bytes"), k.get("blocks_per_sm"), d.get("roofline",{}).get("frac"), "fwd", d["config"].get("forward_order_ms_per_step"))' 2>&1 | tail -1)" >> "$out"
+  echo "$label | $(echo "$line" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); k=d["config"].get("kernel",{}); print(d["ms_per_step"], d["value"], k.get("registers"), k.get("local_bytes"), k.get("blocks_per_sm"), d.get("roofline",{}).get("frac"), "first", d["config"].get("first_call_ms"), "e2e", d["e2e"]["value"])' 2>&1 | tail -1)" >> "$out"
 }
 if [ -n "$spec" ]; then
   while IFS='|' read -r label envs args; do

@@ -101,5 +101,10 @@ REFERENCE_DEVICE_TESTS = ["test/test_vdp.py", "test/test_features.py", "test/tes
 def test_reference_test_suite_passes_unmodified_on_the_gpu(test_file):
     _overlay()
     r = _run(["-m", "pytest", "-q", "-p", "no:cacheprovider", "-W", "ignore", test_file], timeout=1500)
-    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout
+    # 0: everything that ran passed; 5: the file defines no test (test_trajectory.py).  Tests the reference itself marks
+    # as skipped (all of test_observers.py and test_solver.py) stay skipped.
+    assert r.returncode in (0, 5), r.stdout[-4000:] + r.stderr[-2000:]
+    assert " failed" not in r.stdout and " error" not in r.stdout, r.stdout[-2000:]
+    if test_file in ("test/test_vdp.py", "test/test_features.py", "test/test_ornl_thompson_a1.py", "test/test_aux_values.py",
+                     "test/test_opencl_builtins.py", "test/test_runtime.py", "test/test_logger.py", "test/test_xpp_parser.py"):
+        assert " passed" in r.stdout, r.stdout[-2000:]
