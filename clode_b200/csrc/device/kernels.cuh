@@ -518,6 +518,17 @@ clode_interleave_rows(realtype *dst, const realtype *src, const unsigned long lo
     for (size_t r = blockIdx.y; r < rows; r += gridDim.y)
         dst[instance_major ? inst * rows + r : r * n_total + inst] = src[r * count + j];
 }
+
+// upload side of the same: records of `cols` reals per instance (the Python front end's (ensemble, nVar) matrices, moved to
+// the device as they are) into the variable-major device layout dst[c * n + i]
+extern "C" __global__ void __launch_bounds__(256)
+clode_records_to_rows(realtype *dst, const double *src, const unsigned long long n, const unsigned int cols)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (unsigned int c = 0; c < cols; ++c)
+        dst[(size_t)c * n + i] = (realtype)src[i * cols + c];
+}
 #endif // !__CUDACC_EMU__
 
 #ifdef CLODE_WITH_FEATURES

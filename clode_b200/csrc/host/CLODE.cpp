@@ -232,6 +232,10 @@ void CLODE::uploadRows(const cl_double *full, int rows, int which, const char *w
 // host element (row r, instance i) at a[r*rowStride + i*instStride] -> per-shard [rows][count]
 void CLODE::uploadMatrix(const cl_double *a, int rows, size_t rowStride, size_t instStride, int which, const char *where)
 {
+    if (rowStride == 1 && instStride >= (size_t)rows) { // records of `rows` consecutive values: moved as they are, transposed on the GPU
+        forEachShard([&](Shard &s) { return clode_sim_set_records(s.sim, which, a, (size_t)rows, instStride, s.first, s.stride); }, where);
+        return;
+    }
     forEachShard([&](Shard &s) {
         return clode_sim_set_rows(s.sim, which, a, (size_t)rows, rowStride, s.first * instStride, s.stride * instStride);
     }, where);

@@ -449,7 +449,8 @@ struct clode_sim {
     Buffer cost; // 2 x 2 u64: accepted steps in the lower / upper half of the ensemble (block_order auto)
     // cost-sorted chunked execution of the adaptive time loops (kernels.cuh "Scheduling")
     Buffer park_real, park_uint, perm[2], sched_bucket, sched_hist, sched_cursor, sched_state;
-    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr, k_interleave = nullptr;
+    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr, k_interleave = nullptr, k_records = nullptr;
+    Buffer records_tmp; // instance-major upload staging on the device (clode_sim_set_records)
     // page-locked staging ring for strided / converting host transfers (clode_sim_set_rows / get_rows)
     static constexpr size_t kStageBytes = 4u << 20;
     void *stage[2] = {nullptr, nullptr};
@@ -624,7 +625,7 @@ struct clode_sim {
     {
         Buffer *all[] = {&x0, &pars, &xf, &rng, &dt, &tf, &steps, &od_real, &od_uint, &F, &tr_t, &tr_x, &tr_dx, &tr_aux, &n_stored, &queue, &cost,
                          &park_real, &park_uint, &perm[0], &perm[1], &sched_bucket, &sched_hist, &sched_cursor, &sched_state,
-                         &gather_tmp, &gathered,
+                         &gather_tmp, &gathered, &records_tmp,
                          &chunk[0].t, &chunk[0].x, &chunk[0].dx, &chunk[0].aux, &chunk[1].t, &chunk[1].x, &chunk[1].dx, &chunk[1].aux,
                          &rs_real, &rs_uint, &chunk_flags};
         for (Buffer *b : all) release(*b);
@@ -744,15 +745,19 @@ struct clode_sim {
     // Enqueued as ONE stream-ordered sequence without host round trips: the scan kernel leaves the number of live
     // instances and the next attempt budget in device memory (sched_state), the time-loop kernel reads them, and
     // surplus blocks of the full-size grid exit at once.  CLODE_SCHED=off disables it;
-    // CLODE_SCHED="pilot,rounds,fraction,min" overrides the schedule (defaults 256, 8, 0.5, 256).
+    // CLODE_SCHED="pilot,rounds,fraction,min" overrides the schedule (defaults 64 (dopri5) / 256 (bs23), 12, 0.35, = pilot).
     struct Schedule {
         bool on = true;
-        unsigned pilot = 256, rounds = 8, budget_min = 256;
-        float fraction = 0.5f;
+        unsigned pilot = 64, rounds = 12, budget_min = 64;
+        float fraction = 0.35f;
     };
     Schedule schedule() const
     {
         Schedule sc;
+        // The pilot must see enough of an instance's life to rank it: bs23 takes ~4x the steps of dopri5 for the same
+        // tolerance and its first 64 attempts are the common initial transient.  Measured (profiles/r02_schedule_sweep.log):
+        // C2 dopri5 57.9 ms with a 64-attempt pilot against 59.9 with 256; C3 bs23 590 ms with 256 against 603 with 64.
+        if (spec.stepper == 3) sc.pilot = sc.budget_min = 256;
         // only the adaptive steppers diverge; persistent-thread builds balance themselves
         sc.on = (spec.stepper == 3 || spec.stepper == 4) && !spec.work_queue && k_sched_hist && k_sched_scan && k_sched_scatter;
         if (const char *env = std::getenv("CLODE_SCHED")) {
@@ -1084,6 +1089,15 @@ static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scan, s->module, "clode_sched_scan"), "clode_sched_scan"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scatter, s->module, "clode_sched_scatter"), "clode_sched_scatter"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_interleave, s->module, "clode_interleave_rows"), "clode_interleave_rows"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_records, s->module, "clode_records_to_rows"), "clode_records_to_rows"))) return rc;
+    // CUDA loads kernels lazily, on their first launch — several milliseconds each, inside the first call's timed region
+    // otherwise; load everything this module will launch now
+    if (s->d->cuFuncLoad_opt) {
+        CUfunction all[] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory, s->k_layout, s->k_sched_hist, s->k_sched_scan,
+                            s->k_sched_scatter, s->k_interleave, s->k_records};
+        for (CUfunction f : all)
+            if (f) s->d->cuFuncLoad_opt(f);
+    }
     // per-thread local memory (spills + stack) of each time-loop kernel; -1 = kernel not in this program
     CUfunction loops[4] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory};
     for (int k = 0; k < 4; ++k) {
@@ -1629,6 +1643,50 @@ int clode_sim_set_rows(clode_sim *s, int which, const double *host, size_t rows,
     Buffer *b = pick_buffer(s, which, nullptr);
     clode_sim::Scope scope(s);
     return s->transfer_rows(true, *b, const_cast<double *>(host), rows, host_pitch, first, stride, "set_rows");
+}
+
+int clode_sim_set_records(clode_sim *s, int which, const double *host, size_t cols, size_t record_pitch, size_t first, size_t stride)
+{
+    if (!s || !host) return fail(CLODE_ERR_INVALID, "null argument");
+    if (which != CLODE_BUF_X0 && which != CLODE_BUF_PARS) return fail(CLODE_ERR_INVALID, "set_records: only x0 and pars can be written");
+    if (cols == 0 || record_pitch < cols || stride == 0) return fail(CLODE_ERR_INVALID, "set_records: bad record layout");
+    Buffer *b = pick_buffer(s, which, nullptr);
+    const size_t n = s->n;
+    if (!b->ptr || b->bytes != cols * n * s->real_size) return fail(CLODE_ERR_INVALID, "set_records: size mismatch");
+    if (n == 0) return CLODE_OK;
+    if (!s->k_records) return fail(CLODE_ERR_STATE, "set_records: program not built");
+    clode_sim::Scope scope(s);
+    int rc;
+    if ((rc = s->alloc(s->records_tmp, 8 * cols * n, "record staging"))) return rc;
+    if ((rc = s->ensure_stage())) return rc;
+    DriverApi *d = s->d;
+    const bool dense = stride == 1 && record_pitch == cols; // this object's records are one contiguous block
+    const size_t per_chunk = clode_sim::kStageBytes / (8 * cols);
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (size_t k0 = 0; k0 < n; k0 += per_chunk) {
+        const size_t cnt = std::min(per_chunk, n - k0);
+        if (used[slot] && (rc = s->cu(d->cuEventSynchronize(s->stage_done[slot]), "set_records"))) return rc;
+        double *dst = (double *)s->stage[slot];
+        if (dense) {
+            std::memcpy(dst, host + (first + k0) * cols, 8 * cols * cnt);
+        } else {
+            for (size_t k = 0; k < cnt; ++k) {
+                const double *rec = host + (first + (k0 + k) * stride) * record_pitch;
+                for (size_t c = 0; c < cols; ++c) dst[k * cols + c] = rec[c];
+            }
+        }
+        if ((rc = s->cu(d->cuMemcpyHtoDAsync(s->records_tmp.ptr + 8 * cols * k0, dst, 8 * cols * cnt, s->stream), "set_records"))) return rc;
+        if ((rc = s->cu(d->cuEventRecord(s->stage_done[slot], s->stream), "set_records"))) return rc;
+        used[slot] = true;
+        slot ^= 1;
+    }
+    unsigned long long nn = n;
+    unsigned cols_ = (unsigned)cols;
+    void *params[] = {&b->ptr, &s->records_tmp.ptr, &nn, &cols_};
+    if ((rc = s->cu(d->cuLaunchKernel(s->k_records, (unsigned)((n + 255) / 256), 1, 1, 256, 1, 1, 0, s->stream, params, nullptr), "clode_records_to_rows"))) return rc;
+    ++s->launches;
+    return s->cu(d->cuStreamSynchronize(s->stream), "set_records");
 }
 
 int clode_sim_get_rows(clode_sim *s, int which, double *host, size_t rows, size_t host_pitch, size_t first, size_t stride)

@@ -44,6 +44,7 @@ struct DriverApi {
 #define X(name) decltype(&::name) name = nullptr;
     CLODE_DRIVER_FUNCS(X)
 #undef X
+    CUresult (*cuFuncLoad_opt)(CUfunction) = nullptr; // CUDA >= 12.4: load a lazily-loaded kernel now (optional)
     void *handle = nullptr;
     std::string error;
 
@@ -66,6 +67,7 @@ struct DriverApi {
     }
         CLODE_DRIVER_FUNCS(X)
 #undef X
+        cuFuncLoad_opt = reinterpret_cast<decltype(cuFuncLoad_opt)>(dlsym(handle, "cuFuncLoad"));
         CUresult r = cuInit(0);
         if (r != CUDA_SUCCESS) {
             const char *s = nullptr;

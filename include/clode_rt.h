@@ -202,6 +202,12 @@ CLODE_API int clode_sim_set_rows(clode_sim *sim, int which, const double *host, 
                                  size_t first, size_t stride);
 CLODE_API int clode_sim_get_rows(clode_sim *sim, int which, double *host, size_t rows, size_t host_pitch,
                                  size_t first, size_t stride);
+/* Instance-major upload: host holds one RECORD of `cols` consecutive doubles per instance, record k of this simulation
+ * object at host + (first + k*stride) * record_pitch (record_pitch >= cols, in doubles).  The records travel to the
+ * device as they are (one contiguous staging pass, no per-element gather on the CPU) and a kernel transposes them into
+ * the variable-major device buffer `which` (x0 or pars; cols = nVar or nPar). */
+CLODE_API int clode_sim_set_records(clode_sim *sim, int which, const double *host, size_t cols, size_t record_pitch,
+                                    size_t first, size_t stride);
 
 /* The path's one exchange step (north_star: "only a final NVLink gather of features and final states"): the buffers
  * `which` of `n_shards` simulation objects — shard g holding instances g, g+n_shards, ... of a global ensemble of

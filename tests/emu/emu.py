@@ -74,11 +74,11 @@ class EmuLib:
         if not os.path.exists(so):
             cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", f"-ffp-contract={cfg.contract}", "-fno-math-errno",
                    "-fPIC", "-shared", "-w", f"-I{HERE}", f"-I{DEVICE}", *defs,
-                   os.path.join(HERE, "emu_driver.cpp"), "-o", so + ".tmp"]
+                   os.path.join(HERE, "emu_driver.cpp"), "-o", so + f".tmp{os.getpid()}"]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("emu build failed:\n" + " ".join(cmd) + "\n" + r.stderr)
-            os.replace(so + ".tmp", so)
+            os.replace(so + f".tmp{os.getpid()}", so)  # atomic: concurrent test workers may build the same library
         self.lib = ctypes.CDLL(so)
         assert self.lib.emu_args_size() == ctypes.sizeof(KernelArgs)
         lay = (ctypes.c_int * 3)()

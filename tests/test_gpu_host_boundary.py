@@ -36,6 +36,11 @@ def test_cuda_strided_and_transposed_uploads(rt, single):
         sim.set_x0(np.zeros(3 * n))
         sim.set_rows(rt.BUF_X0, x0_matrix.ravel(), 3, 1, first=g * 3, stride=G * 3)  # ... of an instance-major matrix
         assert np.array_equal(sim.get_x0().reshape(3, n), want)
+        sim.set_x0(np.zeros(3 * n))
+        rt._check(sim._lib.clode_sim_set_records(sim._h, rt.BUF_X0, x0_matrix.ctypes.data_as(__import__("ctypes").c_void_p),
+                                                 __import__("ctypes").c_size_t(3), __import__("ctypes").c_size_t(3),
+                                                 __import__("ctypes").c_size_t(g), __import__("ctypes").c_size_t(G)))  # records, transposed on the GPU
+        assert np.array_equal(sim.get_x0().reshape(3, n), want)
         back = np.full(3 * n * G, np.nan)
         sim.get_rows(rt.BUF_X0, back, 3, n * G, first=g, stride=G)
         assert np.array_equal(back.reshape(3, n * G)[:, g::G], want)
@@ -92,7 +97,7 @@ def test_frontend_matrix_path_equals_flat_path_and_results_are_page_locked_views
     Fa = a._device_features                       # (n, nf) matrix, transposed on the GPU
     assert Fa.shape == (n, 6) and Fa.flags.c_contiguous and not Fa.flags.owndata
     assert np.shares_memory(out.F, Fa)            # the record array is a view of it, not a copy
-    assert np.array_equal(out.get_var_max("x"), Fa[:, 0])
+    assert np.array_equal(np.ravel(out.get_var_max("x")), Fa[:, 0])
     b = make()                                    # the same data through the reference's flat (variable-major) calls
     b._integrator.set_problem_data(_as_f(b._device_initial_state), _as_f(b._device_parameters))
     b._integrator.features()
