@@ -18,6 +18,7 @@
 #include <fstream>
 #include <sstream>
 #include <future>
+#include <map>
 #include <mutex>
 #include <string>
 #include <sys/stat.h>
@@ -1556,7 +1557,15 @@ int clode_sim_trajectory_stream(clode_sim *s, size_t chunk_rows, double *t, doub
     return CLODE_OK;
 }
 
-// page-locked host memory for the streamed trajectory's output arrays (copies at full PCIe rate)
+// Page-locked host memory (result arrays handed to numpy, the streamed trajectory's outputs).  The block belongs to the
+// device's primary context, and that context is destroyed — taking its allocations with it — when its last reference is
+// released, e.g. when the last simulation object is closed while a result array is still alive.  Every block therefore
+// holds its own reference on the context until clode_host_free.
+namespace {
+std::mutex g_host_mutex;
+std::map<void *, CUdevice> g_host_blocks;
+} // namespace
+
 void *clode_host_alloc(int device, size_t bytes)
 {
     std::string why;
@@ -1573,8 +1582,13 @@ void *clode_host_alloc(int device, size_t bytes)
     CUresult r = d->cuMemHostAlloc(&p, bytes, CU_MEMHOSTALLOC_PORTABLE);
     CUcontext popped;
     d->cuCtxPopCurrent(&popped);
-    d->cuDevicePrimaryCtxRelease(dev);
-    if (r != CUDA_SUCCESS) { fail(CLODE_ERR_MEMORY, "host_alloc: " + cu_error(d, r)); return nullptr; }
+    if (r != CUDA_SUCCESS) {
+        d->cuDevicePrimaryCtxRelease(dev);
+        fail(CLODE_ERR_MEMORY, "host_alloc: " + cu_error(d, r));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    g_host_blocks[p] = dev; // the context reference is released by clode_host_free
     return p;
 }
 
@@ -1582,7 +1596,24 @@ void clode_host_free(void *p)
 {
     std::string why;
     DriverApi *d = driver(&why);
-    if (d && p) d->cuMemFreeHost(p);
+    if (!d || !p) return;
+    CUdevice dev = 0;
+    bool known = false;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mutex);
+        auto it = g_host_blocks.find(p);
+        if (it != g_host_blocks.end()) { dev = it->second; known = true; g_host_blocks.erase(it); }
+    }
+    if (!known) { d->cuMemFreeHost(p); return; }
+    CUcontext ctx = nullptr;
+    if (d->cuDevicePrimaryCtxRetain(&ctx, dev) == CUDA_SUCCESS) {
+        d->cuCtxPushCurrent(ctx);
+        d->cuMemFreeHost(p);
+        CUcontext popped;
+        d->cuCtxPopCurrent(&popped);
+        d->cuDevicePrimaryCtxRelease(dev); // this call's own reference
+    }
+    d->cuDevicePrimaryCtxRelease(dev);     // the block's reference
 }
 
 int clode_sim_enqueue(clode_sim *s, int kernel, int initialize)

@@ -105,3 +105,31 @@ def test_frontend_matrix_path_equals_flat_path_and_results_are_page_locked_views
     assert np.array_equal(Fa, Fb)
     assert np.array_equal(a.get_final_state(), np.asarray(b._integrator.get_xf_array()).reshape((n, 3), order="F"))
     assert np.array_equal(np.asarray(b._integrator.get_pars_array()).reshape((n, 3), order="F")[:, 0], r)
+
+
+def test_result_arrays_outlive_their_simulator(rt):
+    """a page-locked result block keeps its own reference on the device context: closing the last simulation object
+    (which releases the primary context) must not free memory that a numpy array — or the pool — still holds"""
+    import gc
+
+    import clode_b200 as clode
+    from clode_b200 import build
+    from clode_b200.models import rhs_path
+
+    build.build_all()
+    kept = []
+    for k in range(3):
+        fs = clode.FeatureSimulator(src_file=rhs_path("lorenz63"), variables={"x": 1.0, "y": 1.0, "z": 1.0},
+                                    parameters={"r": 28.0 + k, "s": 10.0, "b": 8.0 / 3.0}, aux=["a"], observer=clode.Observer.basic,
+                                    stepper=clode.Stepper.rk4, single_precision=(k == 1), t_span=(0.0, 1.0), dt=0.01)
+        out = fs.features()
+        kept.append((np.array(out.F["max x"]).copy(), out.F, fs.get_final_state()))
+        del fs, out
+        gc.collect()  # the simulator (and with it the last clode_sim) is gone; the arrays are not
+    for snapshot, F, xf in kept:
+        assert np.array_equal(F["max x"], snapshot) and np.all(np.isfinite(xf))
+    a = rt.pinned_empty(1000)
+    a[:] = 1.0
+    del kept
+    gc.collect()
+    assert a.sum() == 1000.0
