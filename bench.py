@@ -84,19 +84,19 @@ def workload(name: str, n_total: int, index):
                  pars=np.concatenate([np.full(n, 1.5), np.full(n, 3.0), np.full(n, 1.0), np.full(n, 1.0)]),
                  x0=np.concatenate([np.full(n, -60.0), np.zeros(n), np.zeros(n), np.full(n, 0.1)]),
                  desc="C4: lactotroph_noise stochastic Euler features (basicall), per-instance RNG streams, f64")
-    elif name in ("C5", "C5e"):
+    elif name in ("C5", "C5e", "C5d"):
         # Chay-Keizer trajectories: 512 x 512 (gca x kpmca) grid per GPU, 2000 stored points, nout = 1
         side = int(round(n_total ** 0.5))
         gca = 550.0 + 500.0 * (idx // side) / max(side - 1, 1)
         kpmca = 0.095 + 0.06 * (idx % side) / max(side - 1, 1)
-        stepper = "rk4" if name == "C5" else "euler"
+        stepper = {"C5": "rk4", "C5e": "euler", "C5d": "dopri5"}[name]  # BASELINE configs[4]: rk4 (and dopri5); C5e = store-bound variant
         w = dict(model="chay_keizer", stepper=stepper, observer="basic", kind="trajectory", tspan=(0.0, 1000.0),
                  solver=dict(dt=0.5 if name == "C5" else 0.05, dtmax=1.0, abstol=1e-6, reltol=1e-4, max_steps=10000000,
                              max_store=2000, nout=1),
                  observer_params=dict(),
                  pars=np.concatenate([gca, np.full(n, 750.0), kpmca]),
                  x0=np.concatenate([np.full(n, -50.0), np.full(n, 0.01), np.full(n, 0.12)]),
-                 desc=f"C5: Chay-Keizer trajectory, {stepper}, 2000 stored points x 2^18 instances per GPU, nout=1, f64")
+                 desc=f"{name}: Chay-Keizer trajectory, {stepper}, 2000 stored points x 2^18 instances per GPU, nout=1, f64")
     else:
         raise SystemExit(f"unknown workload {name}")
     w["flops_per_step"] = flops_per_step(w["stepper"], w["model"])
@@ -150,7 +150,7 @@ def cpu_reference(wname: str, n_gpus: int, steps: int, warmup: int, sample: int 
     from clode_b200 import sharding
     from clode_b200.models import MODELS
 
-    per_gpu = {"C5": 1 << 18, "C5e": 1 << 18, "C4": 1 << 22}.get(wname, N_PER_GPU)
+    per_gpu = {"C5": 1 << 18, "C5e": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(wname, N_PER_GPU)
     n_total = per_gpu * n_gpus
     sample = min(sample, n_total)
     stride = n_total // sample
@@ -281,7 +281,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_runtime()
 
-    default_n = {"C5": 1 << 18, "C5e": 1 << 18, "C4": 1 << 22}.get(args.workload, N_PER_GPU)
+    default_n = {"C5": 1 << 18, "C5e": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(args.workload, N_PER_GPU)
     n = default_n if args.npts <= 0 else args.npts
     job = Job(args, args.workload, n, world, rank, local, bit_exact=bool(args.bit_exact), shuffle=args.shuffle)
     sim, w = job.sim, job.w
@@ -312,7 +312,7 @@ def run_ours(args):
     def gather_async(k):
         if not dist:
             return
-        ptr, nbytes, _ = sim.device_buffer(_rt.BUF_XF if is_traj else _rt.BUF_F)
+        ptr, nbytes, _ = sim.device_buffer(_rt.BUF_XF if (is_traj or job.transient) else _rt.BUF_F)
         local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
         b = k & 1
         if pending[b] is not None:
@@ -370,6 +370,9 @@ def run_ours(args):
         if is_traj:
             sim.trajectory()       # the e2e result read back is the final state; fetching the 29 GB trajectory itself
             F = sim.get_xf(out_host)  # is a separate API call (CLODEtrajectory::getX), see --stream-rows
+        elif job.transient:
+            sim.transient()
+            F = sim.get_xf(out_host)
         else:
             sim.features(1)
             F = sim.get_f(out_host)
@@ -377,7 +380,7 @@ def run_ours(args):
     gather_drain()
     barrier()
     e2e_s = time.perf_counter() - t0
-    if not is_traj:
+    if not is_traj and not job.transient:
         assert int(F.reshape(nfeat, n)[job.step_row].sum()) == steps_per_pass
     h2d = 8 * n * (nv + npar + 1)
     d2h = 8 * n * nfeat
@@ -392,7 +395,7 @@ def run_ours(args):
     total_steps_per_pass, launches = int(total_steps_per_pass), int(launches)
 
     extras = {}
-    if not args.quick and not is_traj:
+    if not args.quick and not is_traj and not job.transient:
         extras = run_extras(args, job, world, rank, local, dist, barrier, reduce_max_sum)
     if rank != 0:
         if dist:
@@ -583,10 +586,10 @@ def run_extras(args, job, world, rank, local, dist, barrier, reduce_max_sum):
         strong.close()
 
     # ---- the other BASELINE configs, one line each (weak scaling like the headline) ------------------------------
-    for other_name, steps in (("C2l", 3), ("C2t", 3), ("C3", 2), ("C4", 2), ("C5", 3)):
+    for other_name, steps in (("C2l", 3), ("C2t", 3), ("C3", 2), ("C4", 2), ("C5", 3), ("C5d", 3)):
         if other_name == name:
             continue
-        per_gpu = {"C5": 1 << 18, "C4": 1 << 22}.get(other_name, N_PER_GPU)
+        per_gpu = {"C5": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(other_name, N_PER_GPU)
         j = Job(args, other_name, per_gpu, world, rank, local)
         ms, total = timed(j, steps, 1, barrier, reduce_max_sum)
         if rank == 0:

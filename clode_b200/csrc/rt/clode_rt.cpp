@@ -1399,6 +1399,8 @@ static int run_features(clode_sim *s, int initialize, bool blocking)
     clode_sim::Scope scope(s);
     int rc = ensure_feature_buffers(s);
     if (rc) return rc;
+    // all allocations before the first event of the call: cuMemAlloc inside the timed window made a first call look slower
+    if (s->schedule().on && s->n && (rc = s->ensure_sched_buffers())) return rc;
     if (initialize == 1) s->observer_initialized = false;
     // CLODEfeatures::features() (CLODEfeatures.cpp:222-258): warm-up/initialise if needed, then the features pass;
     // both launches are inside the timed region

@@ -23,3 +23,6 @@ except Exception as e:
     print("N=${n} no line:", e)
 PY
 done
+if [ -n "$4" ]; then
+  (timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 2>&1 | tail -1 | cut -c1-700) | tee gpurun_out/${tag}_reference_n2.json
+fi

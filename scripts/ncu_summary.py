@@ -3,8 +3,11 @@ import csv, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # kernel index inside the report
+vals = rows[2 + which]
 d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+print(f"# kernel {which} of {len(rows) - 2} in {rep}")
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "sm__warps_active.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
