@@ -65,6 +65,12 @@ def workload(name: str, n_total: int, index):
                  observer_params=dict(max_event_count=10000),
                  pars=np.concatenate([0.5 + 59.5 * frac, np.full(n, 10.0), np.full(n, 8.0 / 3.0)]),
                  x0=np.ones(3 * n), desc=f"{name}: Lorenz features, dopri5, observer {'basic' if name == 'C2' else 'localmax'}, 2^20 parameter sets per GPU, f64")
+    elif name == "C1":
+        # BASELINE.json configs[0]: Van der Pol transient, rk4, 4096-point mu grid (test_vdp.py's path); the transient kernel
+        w = dict(model="vanderpol", stepper="rk4", observer="basic", kind="features", tspan=(0.0, 100.0),
+                 solver=dict(dt=0.01, dtmax=1.0, abstol=1e-6, reltol=1e-3, max_steps=10000000),
+                 observer_params=dict(), pars=0.1 + 9.9 * frac, x0=np.ones(2 * n),
+                 desc="C1: Van der Pol TRANSIENT kernel, rk4 dt=0.01, t in [0,100], 4096-point mu grid per GPU, f64")
     elif name == "C3":
         # 1024 x 1024 (gcal x gbk) grid, flattened row-major; bs23 + thresh2 (two-pass)
         side = int(round(n_total ** 0.5))
@@ -210,9 +216,9 @@ class Job:
         self.rt, self.name, self.n, self.world, self.rank = _rt, name, n, world, rank
         self.n_total = n * world
         self.index = sharding.interleaved(self.n_total, world, rank)  # rank g owns instances g, g+N, g+2N, ... of ONE global grid
-        self.transient = name == "C2t"  # the transient kernel on the C2 grid (north_star: FMA-pipe utilisation of features AND transient)
-        w = self.w = workload("C2" if self.transient else name, self.n_total, self.index)
-        if self.transient:
+        self.transient = name in ("C2t", "C1")  # the transient kernel (north_star: FMA-pipe utilisation of features AND transient)
+        w = self.w = workload("C2" if name == "C2t" else name, self.n_total, self.index)
+        if name == "C2t":
             w["desc"] = "C2t: Lorenz TRANSIENT kernel, dopri5, 2^20 parameter sets per GPU, f64"
         nv, npar, na, nw = self.dims = MODELS[w["model"]]
         self.is_traj = w["kind"] == "trajectory"
@@ -281,7 +287,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     build.build_runtime()
 
-    default_n = {"C5": 1 << 18, "C5e": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(args.workload, N_PER_GPU)
+    default_n = {"C1": 4096, "C5": 1 << 18, "C5e": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(args.workload, N_PER_GPU)
     n = default_n if args.npts <= 0 else args.npts
     job = Job(args, args.workload, n, world, rank, local, bit_exact=bool(args.bit_exact), shuffle=args.shuffle)
     sim, w = job.sim, job.w
@@ -586,10 +592,10 @@ def run_extras(args, job, world, rank, local, dist, barrier, reduce_max_sum):
         strong.close()
 
     # ---- the other BASELINE configs, one line each (weak scaling like the headline) ------------------------------
-    for other_name, steps in (("C2l", 3), ("C2t", 3), ("C3", 2), ("C4", 2), ("C5", 3), ("C5d", 3)):
+    for other_name, steps in (("C1", 5), ("C2l", 3), ("C2t", 3), ("C3", 2), ("C4", 2), ("C5", 3), ("C5d", 3)):
         if other_name == name:
             continue
-        per_gpu = {"C5": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(other_name, N_PER_GPU)
+        per_gpu = {"C1": 4096, "C5": 1 << 18, "C5d": 1 << 18, "C4": 1 << 22}.get(other_name, N_PER_GPU)
         j = Job(args, other_name, per_gpu, world, rank, local)
         ms, total = timed(j, steps, 1, barrier, reduce_max_sum)
         if rank == 0:
@@ -649,23 +655,31 @@ def frontend_leg(args, job, world, rank, local, dist):
                                         max_steps=sp["max_steps"], observer_max_event_count=opar.get("max_event_count", 100),
                                         observer_x_up_thresh=opar.get("x_up_threshold", 0.3), observer_x_down_thresh=opar.get("x_down_threshold", 0.2),
                                         platform_id=0, device_ids=list(range(world)))
+            split = {"set_ensemble_ms": 0.0, "features_and_results_ms": 0.0}
+
             def one():
+                ta = time.perf_counter()
                 fs.set_ensemble(variables=x0m, parameters=pm)
-                fs.set_solver_parameters(dt=sp["dt"])
+                tb = time.perf_counter()
                 out = fs.features(initialize_observer=True, update_x0=False)
+                tc = time.perf_counter()
+                split["set_ensemble_ms"] += (tb - ta) * 1e3
+                split["features_and_results_ms"] += (tc - tb) * 1e3
                 return out
             for _ in range(2):
                 out = one()
+            split = {k: 0.0 for k in split}
             t0 = time.perf_counter()
             K = max(args.steps // 2, 3)
             for _ in range(K):
                 out = one()
             sec = (time.perf_counter() - t0) / K
+            split = {k: v / K for k, v in split.items()}
             steps_name = [f for f in out.get_feature_names() if "step" in f and "count" in f][0]
             total = int(np.asarray(out.F[steps_name]).sum())
             kernel_ms = fs._integrator.get_last_kernel_ms()
             result = {"value": total / sec, "unit": "instance-steps/s", "ms_per_step": sec * 1e3, "kernel_ms_per_step": kernel_ms,
-                      "fraction_of_kernel_only": kernel_ms / (sec * 1e3), "n_gpus": world, "instances_total": job.n_total,
+                      "fraction_of_kernel_only": kernel_ms / (sec * 1e3), "n_gpus": world, "instances_total": job.n_total, "split": split,
                       "path": "clode_b200.FeatureSimulator(device_ids=[0..N-1]).set_ensemble(numpy) -> features() -> ObserverOutput (record array): "
                               "transposing upload through the page-locked staging ring, NVLink gather + GPU transpose, one D2H into a pooled "
                               "page-locked block that the record array views",

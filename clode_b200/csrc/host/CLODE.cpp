@@ -430,7 +430,8 @@ void CLODE::pushSolverParams()
 void CLODE::setSolverParams(SolverParams<cl_double> newSp)
 {
     sp = newSp;
-    std::fill(dt.begin(), dt.end(), sp.dt);
+    // the reference also fills its host copy of dt here (CLODE.cpp:382) and never uploads it; that copy is only ever
+    // the landing buffer of getDt(), so the fill (64 MB at 8 Mi instances) is skipped
     pushSolverParams();
     lg::debug_("set SolverParams");
 }
