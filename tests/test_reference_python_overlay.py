@@ -108,3 +108,29 @@ def test_reference_test_suite_passes_unmodified_on_the_gpu(test_file):
     if test_file in ("test/test_vdp.py", "test/test_features.py", "test/test_ornl_thompson_a1.py", "test/test_aux_values.py",
                      "test/test_opencl_builtins.py", "test/test_runtime.py", "test/test_logger.py", "test/test_xpp_parser.py"):
         assert " passed" in r.stdout, r.stdout[-2000:]
+
+
+REFERENCE_EXAMPLES = ["dump_device_performance.py", "spike_counting.py", "Ornstein_Uhlenbeck.py", "observe_sine_curve.py",
+                      "find_steady_states.py", "fast_and_slow.py", "phase_response_curve.py", "visualize_events_threshold2.py",
+                      "visualize_events_localmax.py", "visualize_events_nhood2.py", "dump_opencl_info.py"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script", REFERENCE_EXAMPLES)
+def test_reference_example_scripts_run_unmodified_on_the_gpu(script):
+    """the reference's own examples/ — Python right-hand sides through its function converter, 2-D parameter grids, every
+    observer, stochastic runs, and `dump_device_performance.py`, the only performance script the reference ships — executed as
+    they are on the B200 engine (matplotlib is not in the image: a do-nothing stub under tests/stubs stands in for the plots)"""
+    root = _overlay()
+    path = os.path.join(root, "examples", script)
+    if not os.path.exists(path):
+        pytest.skip(script + " not in the overlay")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([OVERLAY, os.path.join(HERE, "stubs")]), MPLBACKEND="Agg",
+               CLODE_CACHE_DIR=os.path.join(REPO, "clode_b200", "_cubin_cache"))
+    r = subprocess.run([sys.executable, "-W", "ignore", path], cwd=OVERLAY, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]
+    if script == "dump_device_performance.py":
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(REPO, "gpurun_out", "reference_dump_device_performance.log"), "w") as f:
+            f.write(r.stdout)
+        assert "Lorenz system, 1000 RK4 steps" in r.stdout and "131072" in r.stdout
