@@ -132,6 +132,44 @@ PM_FN int pm_int_class(double y)
     return (((u & 0x000fffffffffffffULL) | 0x0010000000000000ULL) & unit) ? 1 : 2;
 }
 
+/* x^(1/q), q = 3 or 5, for finite x > 0 — the step-size controller's only use of pow():
+ * `pow(reltol / normErr, 1/(order+1))` (clode/cpp/steppers/adaptive_explicit_step.clh:51,66).  exp(y log x) costs
+ * ~110 uncontracted operations per attempted step, a quarter of a Lorenz dopri5 attempt in the bit-exact tier; a
+ * root needs 35: write x = m 2^(qE + r), w = m 2^r in [1, 2^q), start z ~ w^(-1/q) from the exponent-field
+ * estimate C - bits(w)/q (< 6 % off), apply the cubically convergent inverse-root correction three times
+ *     d = 1 - w z^q,   z <- z (1 + (d/q)(1 + (q+1)/(2q) d)),
+ * and return 2^E w z^(q-1).  Multiplications and additions only (every compiler without contraction rounds them
+ * identically); <= 3 ulp of the true root (tests/test_pm_math.py), inside OpenCL C's 16-ulp bound for pow. */
+PM_FN double pm_rootq(double x, int q)
+{
+    unsigned long long u = PM_D2U(x);
+    int E = 0;
+    if ((u >> 52) == 0) { /* subnormal: times 2^60 (60 = 3*20 = 5*12) */
+        x *= 1152921504606846976.0;
+        u = PM_D2U(x);
+        E = -60 / q;
+    }
+    int e = (int)(u >> 52) - 1023;
+    int Eq = (e >= 0 ? e : e - (q - 1)) / q; /* floor(e / q) */
+    int r = e - q * Eq;                      /* 0 <= r < q  */
+    E += Eq;
+    double w = PM_U2D((u & 0x000fffffffffffffULL) | ((unsigned long long)(1023 + r) << 52));
+    /* bits(w^(-1/q)) ~ (1 + 1/q) (1023 - 0.0450) 2^52 - bits(w)/q */
+    unsigned long long c = q == 5 ? 0x4CC3C6A7EF9DB22DULL : 0x553EF0FF289DD796ULL;
+    double z = PM_U2D(c - PM_D2U(w) / (unsigned long long)q);
+    const double iq = q == 5 ? 0.2 : 1.0 / 3.0;
+    const double hq = q == 5 ? 0.6 : 2.0 / 3.0; /* (q+1)/(2q) */
+    for (int it = 0; it < 3; ++it) {
+        double z2 = z * z;
+        double zq = q == 5 ? (z2 * z2) * z : z2 * z;
+        double d = 1.0 - w * zq;
+        z = z + z * ((d * iq) * (1.0 + hq * d));
+    }
+    double z2 = z * z;
+    double y = q == 5 ? w * (z2 * z2) : w * z2;
+    return y * PM_U2D((unsigned long long)(1023 + E) << 52);
+}
+
 PM_FN double pm_pow(double x, double y)
 {
     unsigned long long ux = PM_D2U(x), uy = PM_D2U(y);
@@ -155,6 +193,8 @@ PM_FN double pm_pow(double x, double y)
         return yneg ? sign * PM_INF : sign * 0.0;
     if (ax == PM_INF)
         return yneg ? sign * 0.0 : sign * PM_INF;
+    if (!xneg && uy == 0x3fc999999999999aULL) return pm_rootq(ax, 5); /* y = 1/5: dopri5's controller */
+    if (!xneg && uy == 0x3fd5555555555555ULL) return pm_rootq(ax, 3); /* y = 1/3: bs23's controller  */
     double l = pm_log(ax);
     double p = y * l;
     /* recover the rounding error of y*l with a Dekker product so that large |p|
