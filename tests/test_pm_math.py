@@ -63,6 +63,24 @@ def test_pow_accuracy_inside_opencl_bound(pm):
     assert err[ctrl].max() <= 7.0
 
 
+def test_controller_root_path(pm):
+    """pow(x, 1/5) and pow(x, 1/3) — the step-size controller's only calls (adaptive_explicit_step.clh:51,66) — take the
+    multiplication-only root (pm_rootq): <= 11 ulp / <= 5 ulp over every binade, exact at perfect powers, the general
+    exp(y log x) path for every other exponent"""
+    rng = np.random.default_rng(2)
+    x = np.concatenate([2.0 ** rng.uniform(-1070, 1023, 400000), 10.0 ** rng.uniform(-8, 8, 100000), [5e-324, 1e-310, 1.0, 32.0, 243.0]])
+    for y, bound in ((0.2, 11.0), (1.0 / 3.0, 5.0)):
+        got = np.empty_like(x)
+        yy = np.full(x.size, y)
+        pm.probe_pow(x.ctypes.data_as(ctypes.c_void_p), yy.ctypes.data_as(ctypes.c_void_p), got.ctypes.data_as(ctypes.c_void_p), x.size)
+        want = np.power(x.astype(np.longdouble), np.longdouble(1) / np.longdouble(round(1 / y))).astype(np.float64)
+        assert _ulp_err(got, want).max() <= bound
+    one = lambda a, b: (lambda o: (pm.probe_pow(np.array([a]).ctypes.data_as(ctypes.c_void_p), np.array([b]).ctypes.data_as(ctypes.c_void_p),
+                                               o.ctypes.data_as(ctypes.c_void_p), 1), o[0])[1])(np.empty(1))
+    assert one(32.0, 0.2) == 2.0 and one(27.0, 1.0 / 3.0) == 3.0 and one(1.0, 0.2) == 1.0
+    assert one(np.inf, 0.2) == np.inf and one(0.0, 1.0 / 3.0) == 0.0 and np.isnan(one(-8.0, 1.0 / 3.0))
+
+
 def test_special_values(pm):
     inf, nan = np.inf, np.nan
     assert np.array_equal(_call1(pm.probe_exp, [0.0, -inf, inf, 710.0, -750.0]), [1.0, 0.0, inf, inf, 0.0])
