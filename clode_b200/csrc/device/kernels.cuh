@@ -529,6 +529,25 @@ clode_records_to_rows(realtype *dst, const double *src, const unsigned long long
     for (unsigned int c = 0; c < cols; ++c)
         dst[(size_t)c * n + i] = (realtype)src[i * cols + c];
 }
+
+// The multi-GPU form of the same upload.  The host array was cut into G CONTIGUOUS chunks, chunk h moved as it is to GPU h
+// (dense DMA, all GPUs at once); this kernel, running on the GPU that owns the interleaved shard g, g+G, ..., PULLS its
+// records out of the chunks — peer loads over NVLink for the chunks that live on other GPUs — and transposes them into
+// the variable-major buffer: the de-interleaving that would cost the host a strided pass over the whole array per shard
+// happens on the GPUs.  src[h] = device pointer of chunk h (records of `cols` doubles), `chunk` = records per chunk.
+struct PeerChunks { const double *src[16]; };
+extern "C" __global__ void __launch_bounds__(256)
+clode_records_pull(realtype *dst, const PeerChunks peers, const unsigned long long n_local, const unsigned int cols,
+                   const unsigned long long first, const unsigned long long stride, const unsigned long long chunk)
+{
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= n_local) return;
+    const size_t i = first + k * stride; // global instance
+    const size_t h = i / chunk;
+    const double *rec = peers.src[h] + (i - h * chunk) * cols;
+    for (unsigned int c = 0; c < cols; ++c)
+        dst[(size_t)c * n_local + k] = (realtype)rec[c];
+}
 #endif // !__CUDACC_EMU__
 
 #ifdef CLODE_WITH_FEATURES

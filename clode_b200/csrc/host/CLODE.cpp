@@ -232,6 +232,30 @@ void CLODE::uploadRows(const cl_double *full, int rows, int which, const char *w
 // host element (row r, instance i) at a[r*rowStride + i*instStride] -> per-shard [rows][count]
 void CLODE::uploadMatrix(const cl_double *a, int rows, size_t rowStride, size_t instStride, int which, const char *where)
 {
+    if (rowStride == 1 && instStride == (size_t)rows && shards().size() > 1 && shards().size() <= 16 &&
+        (size_t)nPts >= shards().size()) {
+        // dense records on several GPUs: contiguous chunk h to GPU h (dense DMA, one host thread per GPU), then every GPU
+        // pulls its interleaved shard out of all chunks with peer loads over NVLink (clode_scatter_records) — instead of
+        // one strided pass over the whole host array per shard
+        const size_t G = shards().size(), chunk = ((size_t)nPts + G - 1) / G;
+        std::vector<clode_sim *> sims;
+        for (auto &s : shards()) sims.push_back(s.sim);
+        std::vector<int> rc(G, CLODE_OK);
+        std::vector<std::string> msg(G);
+        std::vector<std::thread> workers;
+        for (size_t h = 0; h < G; ++h)
+            workers.emplace_back([&, h] {
+                const size_t lo = std::min((size_t)nPts, h * chunk), hi = std::min((size_t)nPts, lo + chunk);
+                rc[h] = clode_sim_stage_records(sims[h], a + lo * rows, hi - lo, (size_t)rows);
+                if (rc[h]) msg[h] = clode_last_error();
+            });
+        for (auto &w : workers) w.join();
+        for (size_t h = 0; h < G; ++h)
+            if (rc[h]) throw std::runtime_error(std::string(where) + ": " + msg[h]);
+        int status = clode_scatter_records(sims.data(), (int)G, which, (size_t)rows, (size_t)nPts);
+        if (status == CLODE_OK) return;
+        lg::warn_("{}: peer scatter unavailable ({}), falling back to per-shard strided uploads", where, clode_last_error());
+    }
     if (rowStride == 1 && instStride >= (size_t)rows) { // records of `rows` consecutive values: moved as they are, transposed on the GPU
         forEachShard([&](Shard &s) { return clode_sim_set_records(s.sim, which, a, (size_t)rows, instStride, s.first, s.stride); }, where);
         return;

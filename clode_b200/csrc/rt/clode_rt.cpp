@@ -450,7 +450,9 @@ struct clode_sim {
     Buffer cost; // 2 x 2 u64: accepted steps in the lower / upper half of the ensemble (block_order auto)
     // cost-sorted chunked execution of the adaptive time loops (kernels.cuh "Scheduling")
     Buffer park_real, park_uint, perm[2], sched_bucket, sched_hist, sched_cursor, sched_state;
-    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr, k_interleave = nullptr, k_records = nullptr;
+    CUfunction k_sched_hist = nullptr, k_sched_scan = nullptr, k_sched_scatter = nullptr, k_interleave = nullptr, k_records = nullptr,
+               k_records_pull = nullptr;
+    size_t staged_records = 0; // records currently in records_tmp (clode_sim_stage_records)
     Buffer records_tmp; // instance-major upload staging on the device (clode_sim_set_records)
     // page-locked staging ring for strided / converting host transfers (clode_sim_set_rows / get_rows)
     static constexpr size_t kStageBytes = 4u << 20;
@@ -1091,11 +1093,12 @@ static int load_module(clode_sim *s, const ProgramSpec &spec, const std::vector<
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_sched_scatter, s->module, "clode_sched_scatter"), "clode_sched_scatter"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_interleave, s->module, "clode_interleave_rows"), "clode_interleave_rows"))) return rc;
     if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_records, s->module, "clode_records_to_rows"), "clode_records_to_rows"))) return rc;
+    if ((rc = s->cu(s->d->cuModuleGetFunction(&s->k_records_pull, s->module, "clode_records_pull"), "clode_records_pull"))) return rc;
     // CUDA loads kernels lazily, on their first launch — several milliseconds each, inside the first call's timed region
     // otherwise; load everything this module will launch now
     if (s->d->cuFuncLoad_opt) {
         CUfunction all[] = {s->k_transient, s->k_init, s->k_features, s->k_trajectory, s->k_layout, s->k_sched_hist, s->k_sched_scan,
-                            s->k_sched_scatter, s->k_interleave, s->k_records};
+                            s->k_sched_scatter, s->k_interleave, s->k_records, s->k_records_pull};
         for (CUfunction f : all)
             if (f) s->d->cuFuncLoad_opt(f);
     }
@@ -1690,7 +1693,8 @@ int clode_sim_set_records(clode_sim *s, int which, const double *host, size_t co
     if (!s->k_records) return fail(CLODE_ERR_STATE, "set_records: program not built");
     clode_sim::Scope scope(s);
     int rc;
-    if ((rc = s->alloc(s->records_tmp, 8 * cols * n, "record staging"))) return rc;
+    if ((rc = s->alloc(s->records_tmp, std::max<size_t>(8 * cols * n, s->records_tmp.bytes), "record staging"))) return rc;
+    s->staged_records = 0;
     if ((rc = s->ensure_stage())) return rc;
     DriverApi *d = s->d;
     const bool dense = stride == 1 && record_pitch == cols; // this object's records are one contiguous block
@@ -1729,6 +1733,79 @@ int clode_sim_set_records(clode_sim *s, int which, const double *host, size_t co
     if ((rc = s->cu(d->cuLaunchKernel(s->k_records, (unsigned)((n + 255) / 256), 1, 1, 256, 1, 1, 0, s->stream, params, nullptr), "clode_records_to_rows"))) return rc;
     ++s->launches;
     return s->cu(d->cuStreamSynchronize(s->stream), "set_records");
+}
+
+int clode_sim_stage_records(clode_sim *s, const double *chunk, size_t n_records, size_t cols)
+{
+    if (!s || (!chunk && n_records)) return fail(CLODE_ERR_INVALID, "null argument");
+    if (cols == 0) return fail(CLODE_ERR_INVALID, "stage_records: cols must be positive");
+    clode_sim::Scope scope(s);
+    int rc;
+    s->staged_records = 0;
+    if (n_records == 0) return CLODE_OK;
+    if ((rc = s->alloc(s->records_tmp, std::max<size_t>(8 * cols * n_records, s->records_tmp.bytes), "record staging"))) return rc;
+    if ((rc = s->ensure_stage())) return rc;
+    DriverApi *d = s->d;
+    const size_t per_chunk = clode_sim::kStageBytes / (8 * cols);
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (size_t k0 = 0; k0 < n_records; k0 += per_chunk) { // memcpy into the ring while the previous piece is on the wire
+        const size_t cnt = std::min(per_chunk, n_records - k0);
+        if (used[slot] && (rc = s->cu(d->cuEventSynchronize(s->stage_done[slot]), "stage_records"))) return rc;
+        std::memcpy(s->stage[slot], chunk + k0 * cols, 8 * cols * cnt);
+        if ((rc = s->cu(d->cuMemcpyHtoDAsync(s->records_tmp.ptr + 8 * cols * k0, s->stage[slot], 8 * cols * cnt, s->stream), "stage_records"))) return rc;
+        if ((rc = s->cu(d->cuEventRecord(s->stage_done[slot], s->stream), "stage_records"))) return rc;
+        used[slot] = true;
+        slot ^= 1;
+    }
+    if ((rc = s->cu(d->cuStreamSynchronize(s->stream), "stage_records"))) return rc;
+    s->staged_records = n_records;
+    return CLODE_OK;
+}
+
+int clode_scatter_records(clode_sim *const *shards, int n_shards, int which, size_t cols, size_t n_total)
+{
+    if (!shards || n_shards < 1 || n_shards > 16) return fail(CLODE_ERR_INVALID, "scatter_records: 1..16 shards");
+    if (which != CLODE_BUF_X0 && which != CLODE_BUF_PARS) return fail(CLODE_ERR_INVALID, "scatter_records: only x0 and pars can be written");
+    const size_t G = (size_t)n_shards, chunk = (n_total + G - 1) / G;
+    struct { CUdeviceptr src[16]; } peers;
+    std::memset(&peers, 0, sizeof peers);
+    for (int h = 0; h < n_shards; ++h) {
+        clode_sim *s = shards[h];
+        if (!s) return fail(CLODE_ERR_INVALID, "scatter_records: null shard");
+        const size_t lo = std::min(n_total, (size_t)h * chunk), hi = std::min(n_total, lo + chunk);
+        if (s->staged_records != hi - lo) return fail(CLODE_ERR_STATE, "scatter_records: stage every chunk first (clode_sim_stage_records)");
+        peers.src[h] = s->records_tmp.ptr;
+    }
+    int rc;
+    for (int g = 0; g < n_shards; ++g) { // every GPU pulls its own shard; the launches run concurrently
+        clode_sim *s = shards[g];
+        const size_t want = n_total > (size_t)g ? (n_total - g + G - 1) / G : 0;
+        if (s->n != want) return fail(CLODE_ERR_INVALID, "scatter_records: shard sizes do not form an interleaved partition of n_total");
+        if (want == 0) continue;
+        Buffer *b = pick_buffer(s, which, nullptr);
+        if (!b->ptr || b->bytes != cols * want * s->real_size) return fail(CLODE_ERR_INVALID, "scatter_records: size mismatch");
+        if (!s->k_records_pull) return fail(CLODE_ERR_STATE, "scatter_records: program not built");
+        clode_sim::Scope scope(s);
+        for (int h = 0; h < n_shards; ++h)
+            if (shards[h]->device != s->device) {
+                CUresult pr = s->d->cuCtxEnablePeerAccess(shards[h]->ctx, 0);
+                if (pr != CUDA_SUCCESS && pr != CUDA_ERROR_PEER_ACCESS_ALREADY_ENABLED)
+                    return s->cu(pr, "cuCtxEnablePeerAccess (scatter_records needs peer access between the GPUs)");
+            }
+        unsigned long long n_local = want, first = (unsigned long long)g, stride = G, chunk_ = chunk;
+        unsigned cols_ = (unsigned)cols;
+        void *params[] = {&b->ptr, &peers, &n_local, &cols_, &first, &stride, &chunk_};
+        if ((rc = s->cu(s->d->cuLaunchKernel(s->k_records_pull, (unsigned)((want + 255) / 256), 1, 1, 256, 1, 1, 0, s->stream, params, nullptr), "clode_records_pull"))) return rc;
+        ++s->launches;
+    }
+    for (int g = 0; g < n_shards; ++g) { // the chunks may be overwritten only after every GPU has read them
+        clode_sim *s = shards[g];
+        clode_sim::Scope scope(s);
+        if ((rc = s->cu(s->d->cuStreamSynchronize(s->stream), "scatter_records"))) return rc;
+    }
+    for (int g = 0; g < n_shards; ++g) shards[g]->staged_records = 0;
+    return CLODE_OK;
 }
 
 int clode_sim_get_rows(clode_sim *s, int which, double *host, size_t rows, size_t host_pitch, size_t first, size_t stride)

@@ -209,6 +209,14 @@ CLODE_API int clode_sim_get_rows(clode_sim *sim, int which, double *host, size_t
 CLODE_API int clode_sim_set_records(clode_sim *sim, int which, const double *host, size_t cols, size_t record_pitch,
                                     size_t first, size_t stride);
 
+/* The same for an ensemble spread over several GPUs, without a strided pass over the host array per shard: the host array
+ * of n_total records is cut into n_shards CONTIGUOUS chunks of ceil(n_total / n_shards) records; clode_sim_stage_records
+ * moves chunk h to shards[h]'s GPU as it is (call it for every shard, from one host thread per GPU), then
+ * clode_scatter_records lets every GPU pull the records of ITS interleaved shard out of all chunks with peer loads over
+ * NVLink and transpose them into its variable-major buffer `which` (x0 or pars). */
+CLODE_API int clode_sim_stage_records(clode_sim *sim, const double *chunk, size_t n_records, size_t cols);
+CLODE_API int clode_scatter_records(clode_sim *const *shards, int n_shards, int which, size_t cols, size_t n_total);
+
 /* The path's one exchange step (north_star: "only a final NVLink gather of features and final states"): the buffers
  * `which` of `n_shards` simulation objects — shard g holding instances g, g+n_shards, ... of a global ensemble of
  * n_total — are copied device-to-device over NVLink to `shards[0]`'s GPU (cuMemcpyPeerAsync, ordered behind each shard's

@@ -133,3 +133,34 @@ def test_result_arrays_outlive_their_simulator(rt):
     del kept
     gc.collect()
     assert a.sum() == 1000.0
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_cuda_contiguous_chunks_plus_peer_pull_equals_strided_upload(rt, single):
+    """the multi-GPU upload: contiguous chunk h of the host matrix to shard h (clode_sim_stage_records), then every shard pulls
+    its interleaved instances out of all chunks (clode_scatter_records; peer loads over NVLink when the shards sit on
+    different GPUs — on one GPU here, on two in test_in_process_*) — same device contents as the strided per-shard upload"""
+    import ctypes
+
+    n_total, G = 100003, 3  # ragged: the last chunk is shorter, the shards differ in size
+    rng = np.random.default_rng(1)
+    m = rng.standard_normal((n_total, 3))
+    shards = []
+    for g in range(G):
+        s = _sim(rt, single=single)
+        cnt = len(range(g, n_total, G))
+        s.set_problem(np.zeros(3 * cnt), np.zeros(3 * cnt))
+        shards.append(s)
+    chunk = -(-n_total // G)
+    for h, s in enumerate(shards):
+        part = np.ascontiguousarray(m[h * chunk:(h + 1) * chunk])
+        rt._check(s._lib.clode_sim_stage_records(s._h, part.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(part.shape[0]), ctypes.c_size_t(3)))
+    handles = (ctypes.c_void_p * G)(*[s._h for s in shards])
+    rt._check(rt.lib().clode_scatter_records(handles, G, rt.BUF_X0, ctypes.c_size_t(3), ctypes.c_size_t(n_total)))
+    cast = (lambda a: a.astype(np.float32).astype(np.float64)) if single else (lambda a: a)
+    for g, s in enumerate(shards):
+        assert np.array_equal(s.get_x0().reshape(3, -1), cast(m[g::G].T))
+    # staging is consumed: a second scatter without new chunks is a state error, not stale data
+    assert rt.lib().clode_scatter_records(handles, G, rt.BUF_X0, ctypes.c_size_t(3), ctypes.c_size_t(n_total)) != 0
+    for s in shards:
+        s.close()

@@ -87,7 +87,7 @@ def test_nvrtc_compiles_every_stepper_observer_pair(rt, stepper, observer, tmp_p
     functions = re.findall(r"Function (\w+):", usage)
     assert sorted(functions) == sorted(["clode_transient", "clode_initialize_observer", "clode_features",
                                         "clode_trajectory", "clode_observer_layout", "clode_sched_histogram",
-                                        "clode_sched_scan", "clode_sched_scatter", "clode_interleave_rows", "clode_records_to_rows"]), functions
+                                        "clode_sched_scan", "clode_sched_scatter", "clode_interleave_rows", "clode_records_to_rows", "clode_records_pull"]), functions
 
 
 def test_nvrtc_other_variants(rt):
