@@ -309,32 +309,20 @@ def run_ours(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         return mx.tolist(), sm.tolist()
 
-    # the one exchange step of the path: results of every shard to rank 0 over NVLink (NCCL gather).  Issued
-    # asynchronously from a staging copy of the result, so that it overlaps the next pass; completed before the
-    # staging buffer is reused and at the end of the timed region.
-    stage = [None, None]
-    pending = [None, None]
+    # the one exchange step of the path: results of every shard to rank 0 over NVLink (NCCL gather), issued asynchronously
+    # from a staging copy so that it overlaps the next pass (clode_b200/sharding.py PipelinedGather)
+    gatherer = sharding.PipelinedGather(nfeat, n_total) if dist else None
 
     def gather_async(k):
         if not dist:
             return
         ptr, nbytes, _ = sim.device_buffer(_rt.BUF_XF if (is_traj or job.transient) else _rt.BUF_F)
-        local_f = torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}")
-        b = k & 1
-        if pending[b] is not None:
-            pending[b].wait()
-        if stage[b] is None:
-            stage[b] = torch.empty_like(local_f)
-        stage[b].copy_(local_f)
-        parts = [torch.empty_like(stage[b]) for _ in range(world)] if rank == 0 else None
-        pending[b] = dist.gather(stage[b], parts, dst=0, async_op=True)
+        gatherer.submit(torch.as_tensor(_CudaArray(ptr, nbytes // 8, "<f8"), device=f"cuda:{local}"))
 
     def gather_drain():
-        for b in (0, 1):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+        out = gatherer.drain() if dist else None
         torch.cuda.synchronize()
+        return out
 
     # ---- warm-up, then K timed steps with inputs resident in HBM ------------------------------
     W = max(args.warmup, 3)
@@ -383,11 +371,13 @@ def run_ours(args):
             sim.features(1)
             F = sim.get_f(out_host)
         gather_async(k)
-    gather_drain()
+    gathered = gather_drain()
     barrier()
     e2e_s = time.perf_counter() - t0
     if not is_traj and not job.transient:
         assert int(F.reshape(nfeat, n)[job.step_row].sum()) == steps_per_pass
+        if gathered is not None:  # rank 0: the gathered global matrix carries every rank's accepted steps
+            gathered_steps = int(gathered.view(nfeat, n_total)[job.step_row].sum().item())
     h2d = 8 * n * (nv + npar + 1)
     d2h = 8 * n * nfeat
 
@@ -399,6 +389,8 @@ def run_ours(args):
     (dev_ms, wall_ms, e2e_s), (_, _, _) = reduce_max_sum([dev_ms, wall_ms, e2e_s])
     _, (total_steps_per_pass, launches) = reduce_max_sum([float(steps_per_pass), float(launches)])
     total_steps_per_pass, launches = int(total_steps_per_pass), int(launches)
+    if dist and rank == 0 and not is_traj and not job.transient:
+        assert gathered_steps == total_steps_per_pass, (gathered_steps, total_steps_per_pass)
 
     extras = {}
     if not args.quick and not is_traj and not job.transient:

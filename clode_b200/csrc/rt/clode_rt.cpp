@@ -474,6 +474,13 @@ struct clode_sim {
 
     float last_ms = 0.f;
     uint64_t launches = 0;
+    // Launch-argument blocks travel from a ring of PAGE-LOCKED slots: the copy into the module's __constant__ block is
+    // then a true in-stream DMA (a pageable source makes cuMemcpyHtoDAsync stage — and possibly synchronise — first), so a
+    // whole schedule of launches is enqueued without the host ever waiting.  A slot is reused only after the stream
+    // has been synchronised past its previous use.
+    static constexpr unsigned kArgSlots = 64;
+    KernelArgs *args_ring = nullptr;
+    unsigned args_next = 0, args_in_flight = 0;
 
     struct Scope { // make the context current for the duration of a call
         clode_sim *s;
@@ -686,6 +693,7 @@ struct clode_sim {
         pending = false;
         int rc = cu(d->cuStreamSynchronize(stream), what);
         if (rc) return rc;
+        args_in_flight = 0;
         d->cuEventElapsedTime(&last_ms, ev0, ev1);
         return CLODE_OK;
     }
@@ -731,8 +739,15 @@ struct clode_sim {
             a.block_order = 0;
         }
         // arguments go to the module's __constant__ block, ordered in-stream before the launch
-        // (pageable source: the driver stages the bytes before cuMemcpyHtoDAsync returns)
-        if ((rc = cu(d->cuMemcpyHtoDAsync(args_symbol, &a, sizeof a, stream), "upload kernel arguments"))) return rc;
+        if (!args_ring && (rc = cu(d->cuMemHostAlloc((void **)&args_ring, sizeof(KernelArgs) * kArgSlots, 0), "argument ring"))) return rc;
+        if (args_in_flight >= kArgSlots) { // every slot may still be read by a queued copy: drain before wrapping around
+            if ((rc = cu(d->cuStreamSynchronize(stream), "argument ring"))) return rc;
+            args_in_flight = 0;
+        }
+        KernelArgs *slot = &args_ring[args_next++ % kArgSlots];
+        ++args_in_flight;
+        *slot = a;
+        if ((rc = cu(d->cuMemcpyHtoDAsync(args_symbol, slot, sizeof a, stream), "upload kernel arguments"))) return rc;
         if (first && (rc = cu(d->cuEventRecord(ev0, stream), "cuEventRecord"))) return rc;
         if ((rc = cu(d->cuLaunchKernel(f, grid, 1, 1, spec.block, 1, 1, (unsigned)dynamic_smem(f), stream, nullptr, nullptr), what))) return rc;
         ++launches;
@@ -1049,6 +1064,7 @@ int clode_sim_destroy(clode_sim *s)
         s->free_ensemble();
         if (s->module) s->d->cuModuleUnload(s->module);
         if (s->flags_host) s->d->cuMemFreeHost(s->flags_host);
+        if (s->args_ring) s->d->cuMemFreeHost(s->args_ring);
         for (int k = 0; k < 2; ++k) {
             if (s->stage[k]) s->d->cuMemFreeHost(s->stage[k]);
             if (s->stage_done[k]) s->d->cuEventDestroy(s->stage_done[k]);

@@ -105,3 +105,60 @@ def gather_rows(local, rows: int, n_total: int, dst: int = 0):
         if phi > plo:
             out[:, plo:phi] = part.view(rows, widest)[:, : phi - plo]
     return out.reshape(-1)
+
+
+class PipelinedGather:
+    """The exchange step of the one-process-per-GPU path, overlapped with the next pass: `submit(local)` copies this rank's
+    result matrix into one of two staging tensors and starts an ASYNCHRONOUS gather to rank `dst` (NCCL over NVLink for CUDA
+    tensors, gloo for CPU tensors in the tests); the caller goes on with the next pass while the bytes move.  A staging
+    tensor is reused only after its previous gather has completed; `drain()` completes what is in flight and returns the
+    last gathered matrix in the global interleaved layout ([rows][n_total] flat) on `dst`, None elsewhere.
+    Ranks hold interleaved shards (rank g: instances g, g+world, ...)."""
+
+    def __init__(self, rows: int, n_total: int, dst: int = 0):
+        import torch.distributed as dist
+
+        self.rows, self.n_total, self.dst = rows, n_total, dst
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.widest = -(-n_total // self.world)
+        self.mine = len(range(self.rank, n_total, self.world))
+        self.stage = [None, None]
+        self.parts = [None, None]
+        self.work = [None, None]
+        self.k = 0
+        self.last = None
+
+    def submit(self, local):
+        import torch
+        import torch.distributed as dist
+
+        b = self.k & 1
+        self.k += 1
+        if self.work[b] is not None:
+            self.work[b].wait()
+            self.work[b] = None
+        if self.stage[b] is None:
+            self.stage[b] = torch.zeros(self.rows * self.widest, dtype=local.dtype, device=local.device)
+            if self.rank == self.dst:
+                self.parts[b] = [torch.empty_like(self.stage[b]) for _ in range(self.world)]
+        if self.mine:
+            self.stage[b].view(self.rows, self.widest)[:, :self.mine].copy_(local.view(self.rows, self.mine))
+        self.work[b] = dist.gather(self.stage[b], self.parts[b], dst=self.dst, async_op=True)
+        self.last = b
+
+    def drain(self):
+        import torch
+
+        for b in (0, 1):
+            if self.work[b] is not None:
+                self.work[b].wait()
+                self.work[b] = None
+        if self.last is None or self.rank != self.dst:
+            return None
+        parts = self.parts[self.last]
+        out = torch.empty(self.rows, self.n_total, dtype=parts[0].dtype, device=parts[0].device)
+        for g, part in enumerate(parts):
+            cnt = len(range(g, self.n_total, self.world))
+            if cnt:
+                out[:, g::self.world] = part.view(self.rows, self.widest)[:, :cnt]
+        return out.reshape(-1)
