@@ -302,11 +302,26 @@ int assemble_ptx(const std::string &ptx, std::vector<char> &cubin, std::string &
     return CLODE_OK;
 }
 
+// Double literals through the constant bank (ptx_pass.hpp hoist_f64_immediates)?  Measured per workload
+// (profiles/r02_imm_hoist_ab.log): the pass removes 4-6 % of the loop's instructions everywhere, but only the fixed-step
+// trajectory kernel gets faster for it (C5 rk4 16.01 -> 15.51 ms); the features kernels are within +-0.5 % (the UMOVs it
+// removes ride the uniform datapath, the constant operands it adds go through the constant cache).  Default: on for
+// programs without a features kernel, off otherwise; CLODE_IMM_HOIST=0|1 overrides (part of the cache key).
+bool hoist_literals(const ProgramSpec &s)
+{
+    if (const char *env = std::getenv("CLODE_IMM_HOIST")) {
+        if (*env == '0') return false;
+        if (*env == '1') return true;
+    }
+    return !(s.kernels & CLODE_KERNEL_FEATURES);
+}
+
 int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &log)
 {
     // cache lookup
     std::string key_src = full_source(s);
-    if (s.const_div) key_src += ptxas_shim() ? "// ptx pass v1, assembled by libclode_ptxas\n" : "// ptx pass v1, assembled by nvJitLink\n";
+    if (s.const_div) key_src += ptxas_shim() ? "// ptx pass v2, assembled by libclode_ptxas\n" : "// ptx pass v2, assembled by nvJitLink\n";
+    if (s.const_div && hoist_literals(s)) key_src += "// double literals through the constant bank\n";
     uint64_t h1 = fnv1a(key_src, 1469598103934665603ull), h2 = fnv1a(key_src, 0x9e3779b97f4a7c15ull);
     char name[64];
     std::snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
@@ -362,11 +377,17 @@ int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &lo
         rtc->nvrtcGetPTX(prog, &ptx[0]);
         rtc->nvrtcDestroyProgram(&prog);
         while (!ptx.empty() && ptx.back() == '\0') ptx.pop_back();
-        int replaced = 0;
+        int replaced = 0, hoisted = 0;
         ptx = rewrite_constant_divisions(ptx, &replaced);
+        if (hoist_literals(s)) ptx = hoist_f64_immediates(ptx, &hoisted);
+        if (const char *dump = std::getenv("CLODE_DUMP_PTX")) { // development aid: the PTX as it goes to ptxas
+            std::ofstream f(dump);
+            f << ptx;
+        }
         int rc = assemble_ptx(ptx, cubin, log);
         if (rc) return rc;
-        log += "\n(ptx pass: " + std::to_string(replaced) + " divisions by a literal constant rewritten)";
+        log += "\n(ptx pass: " + std::to_string(replaced) + " divisions by a literal constant rewritten, " + std::to_string(hoisted) +
+               " double literals moved to the constant bank)";
     } else {
         r = rtc->nvrtcGetCUBINSize(prog, &size);
         if (r != NVRTC_SUCCESS || size == 0) {

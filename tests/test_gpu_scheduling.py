@@ -95,3 +95,31 @@ def test_cuda_schedule_continuation_and_two_pass_cost_reuse(rt):
             g.close()
     assert_bit_equal(out["on"][0], out["off"][0], "two-pass features, scheduled vs off")
     assert_bit_equal(out["on"][1], out["off"][1], "continued features, scheduled vs off")
+
+
+@pytest.mark.parametrize("model, stepper, observer, tspan, dtmax", [("lactotroph", "bs23", "thresh2", (0.0, 1500.0), 100.0),
+                                                                     ("lorenz63", "dopri5", "basic", (0.0, 20.0), 1.0),
+                                                                     ("lactotroph_noise", "seuler", "basicall", (0.0, 20.0), 1.0)])
+def test_cuda_literals_through_the_constant_bank_do_not_change_results(rt, model, stepper, observer, tspan, dtmax):
+    """csrc/rt/ptx_pass.hpp hoist_f64_immediates: double literals become constant-bank operands instead of UMOV pairs —
+    same values, same operations, so the production build's results are bit-identical with the pass off"""
+    n = 3 * 128 + 11
+    _, x0, pars = ensemble(model, n)
+    sp = Solver(dt=0.01, dtmax=dtmax, abstol=1e-6, reltol=1e-5, max_steps=1000000)
+    op = Observer(max_event_count=200, x_up_threshold=0.3, x_down_threshold=0.2)
+    out = {}
+    for name, env in (("hoist", "1"), ("plain", "0")):
+        old = os.environ.get("CLODE_IMM_HOIST")
+        os.environ["CLODE_IMM_HOIST"] = env
+        try:
+            g = GpuRun(rt, model, stepper, observer, bit_exact=False)
+            log = g.sim.build_log() if hasattr(g.sim, "build_log") else ""
+            g.setup(tspan, x0, pars, sp, op, seed=1)
+            out[name] = g.features()
+            g.close()
+        finally:
+            if old is None:
+                os.environ.pop("CLODE_IMM_HOIST", None)
+            else:
+                os.environ["CLODE_IMM_HOIST"] = old
+    assert_bit_equal(out["hoist"], out["plain"], f"{model}: literals through the constant bank")
