@@ -82,6 +82,7 @@ struct ProgramSpec {
     int kernels = CLODE_KERNEL_TRANSIENT;
     bool bit_exact = false, work_queue = false, staged = false, obs_smem = false;
     bool ext_smem = false;    // extents / means of the multi-variable observers in shared memory (observers.cuh)
+    bool ext_smem_auto = false; // ... decided by clode_sim_build from the spill size of the features kernel
     bool library_exp = false; // keep CUDA's exp in production double builds (default: device/fast_exp.cuh)
     bool const_div = true; // ptx_pass.hpp: divisions by literal constants without the Newton refinement of the literal
     int block = 128, min_blocks = 4;
@@ -113,8 +114,12 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     {
+        // extents of the multi-variable observers in shared memory: forced by CLODE_EXT_SMEM=1, forbidden by =0, otherwise
+        // decided at build time from the features kernel's spill size (clode_sim_build)
         const char *env = std::getenv("CLODE_EXT_SMEM");
-        s.ext_smem = env && *env == '1' && (s.kernels & CLODE_KERNEL_FEATURES) && s.observer != 0 && !s.obs_smem;
+        const bool possible = (s.kernels & CLODE_KERNEL_FEATURES) && s.observer != 0 && !s.obs_smem;
+        s.ext_smem = env && *env == '1' && possible;
+        s.ext_smem_auto = !(env && (*env == '0' || *env == '1')) && possible;
     }
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
@@ -1195,6 +1200,22 @@ int clode_sim_build(clode_sim *s, const clode_program_desc *desc)
     std::string log;
     int chosen[4] = {0, 0, 0, 0};
     int local[4] = {-1, -1, -1, -1};
+    // Where do the extents (5 nVar + 3 nAux running extremes / means) of the multi-variable observers live?  In registers
+    // they are free for the light kernels (C4 basicall: no spills; moving them to shared memory costs 21 %), but a
+    // features kernel that already spills several hundred bytes (C3 thresh2: 536 B at 128 registers) runs 5 % faster with
+    // them in shared memory — on sorted and shuffled grids alike (profiles/r02_c3_scheduling_sweep.log: 591.9 -> 563.7 ms,
+    // 627 -> 593 shuffled; C2 localmax with 80 B of spills: 85.6 -> 92.5, i.e. worse).  Rule: probe the features kernel at
+    // 16 warps/SM; at >= 256 B of local memory per thread the extents go to shared memory.
+    if (spec.ext_smem_auto && desc->min_blocks_per_sm == 0) {
+        ProgramSpec probe = spec;
+        probe.min_blocks = std::max(1, 512 / spec.block);
+        std::vector<char> cubin;
+        rc = compile_spec(probe, cubin, log);
+        s->build_log = rc ? g_error : log;
+        if (rc) return rc;
+        if ((rc = load_module(s, probe, cubin, local))) return rc;
+        if (local[2] >= 256) spec.ext_smem = true;
+    }
     for (size_t k = 0; k < candidates.size(); ++k) {
         spec.min_blocks = candidates[k];
         std::vector<char> cubin;
