@@ -141,7 +141,19 @@ CLODE_DEV realtype pick3(const realtype v[3], int at) { return at == 0 ? v[0] : 
 // so that the compiler does not promote the words back into registers for the whole time loop.
 #if defined(CLODE_EXT_SMEM) && !defined(CLODE_OBS_SMEM) && !defined(__CUDACC_EMU__)
 #define CLODE_EXT_IN_SMEM 1
-__shared__ volatile realtype clode_ext_smem[5 * NV + 3 * NA_][CLODE_BLOCK];
+// thresh2 additionally keeps its four Schmitt-trigger thresholds there: written once when the observer is armed,
+// read (two of them) on every accepted step of the features pass
+#if defined(USE_OBSERVER_THRESHOLD_2)
+#define CLODE_EXT_EXTRA_ROWS 4
+#else
+#define CLODE_EXT_EXTRA_ROWS 0
+#endif
+__shared__ volatile realtype clode_ext_smem[5 * NV + 3 * NA_ + CLODE_EXT_EXTRA_ROWS][CLODE_BLOCK];
+template <int ROW> struct ExtScalar { // one per-thread real in the shared array, usable like a realtype member
+    __device__ __forceinline__ operator realtype() const { return clode_ext_smem[ROW][threadIdx.x]; }
+    __device__ __forceinline__ ExtScalar &operator=(const realtype v) { clode_ext_smem[ROW][threadIdx.x] = v; return *this; }
+    __device__ __forceinline__ ExtScalar &operator=(const ExtScalar &o) { return *this = (realtype)o; }
+};
 template <int BASE, int STRIDE> struct ExtField {
     __device__ __forceinline__ volatile realtype &operator[](int j) const { return clode_ext_smem[BASE + STRIDE * j][threadIdx.x]; }
 };
@@ -737,7 +749,13 @@ struct Observer {
     realtype t_up[NS_], t_down[NS_];
     Tri peaks_stat, period, up_time, down_time, duty, dip, step_dt;
     realtype down_mean;
-    realtype g_xmax, g_xmin, g_dxmax, g_dxmin, x_up, x_down, dx_up, dx_down;
+    realtype g_xmax, g_xmin, g_dxmax, g_dxmin;
+#if CLODE_EXT_IN_SMEM
+    ExtScalar<5 * NV + 3 * NA_ + 0> x_up; ExtScalar<5 * NV + 3 * NA_ + 1> x_down;
+    ExtScalar<5 * NV + 3 * NA_ + 2> dx_up; ExtScalar<5 * NV + 3 * NA_ + 3> dx_down;
+#else
+    realtype x_up, x_down, dx_up, dx_down;
+#endif
     realtype t_start, t_last_event, t_this_down, x_last_min;
     unsigned int peaks, steps, events, up;
 
@@ -753,7 +771,7 @@ struct Observer {
         step_dt.reset();
         down_mean = ZERO;
         g_xmax = -BIG_REAL; g_xmin = BIG_REAL; g_dxmax = -BIG_REAL; g_dxmin = BIG_REAL;
-        x_up = x_down = dx_up = dx_down = ZERO;
+        x_up = ZERO; x_down = ZERO; dx_up = ZERO; dx_down = ZERO;
         t_start = I.t; t_last_event = ZERO; t_this_down = ZERO; x_last_min = BIG_REAL;
         peaks = steps = events = up = 0;
     }
@@ -767,11 +785,12 @@ struct Observer {
     __device__ __forceinline__ void arm(const Instance &I, const ObserverParams &op)
     {
         const realtype amp = g_xmax - g_xmin;
-        x_up = g_xmin + op.xUpThresh * amp;
-        x_down = op.xDownThresh > ZERO ? g_xmin + op.xDownThresh * amp : x_up;
+        const realtype xu = g_xmin + op.xUpThresh * amp;
+        x_up = xu;
+        x_down = op.xDownThresh > ZERO ? g_xmin + op.xDownThresh * amp : xu;
         dx_up = op.dxUpThresh * g_dxmax;
         dx_down = op.dxDownThresh > ZERO ? op.dxDownThresh * g_dxmin : g_dxmin;
-        up = I.x[E_VAR_IX] > x_up ? 1 : 0;
+        up = I.x[E_VAR_IX] > xu ? 1 : 0;
     }
     __device__ __forceinline__ void update(const Instance &I, const ObserverParams &)
     {
@@ -904,7 +923,8 @@ struct Observer {
         peaks_stat.visit(v); period.visit(v); up_time.visit(v); down_time.visit(v); duty.visit(v); dip.visit(v);
         step_dt.visit(v);
         v(down_mean);
-        v(g_xmax); v(g_xmin); v(g_dxmax); v(g_dxmin); v(x_up); v(x_down); v(dx_up); v(dx_down);
+        v(g_xmax); v(g_xmin); v(g_dxmax); v(g_dxmin);
+        Extents::visit_one(v, x_up); Extents::visit_one(v, x_down); Extents::visit_one(v, dx_up); Extents::visit_one(v, dx_down);
         v(t_start); v(t_last_event); v(t_this_down); v(x_last_min);
         v(peaks); v(steps); v(events); v(up);
     }
