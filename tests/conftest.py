@@ -72,6 +72,15 @@ def _precompile_only():
         blocks = [prog.min_blocks_per_sm] if prog.min_blocks_per_sm else ([8, 5, 4] if prog.single_precision else [5, 4])
         for m in blocks:
             _rt.compile_program(dataclasses.replace(prog, min_blocks_per_sm=m))
+        # the runtime moves the extents of a multi-variable observer to shared memory when the features kernel spills
+        # (clode_sim_build); which way it goes is only known on the GPU, so both variants are put into the cache
+        if prog.observer != "basic" and (prog.kernels & _rt.KERNEL_FEATURES) and not prog.observer_in_shared and "CLODE_EXT_SMEM" not in os.environ:
+            os.environ["CLODE_EXT_SMEM"] = "1"
+            try:
+                for m in blocks:
+                    _rt.compile_program(dataclasses.replace(prog, min_blocks_per_sm=m))
+            finally:
+                del os.environ["CLODE_EXT_SMEM"]
         pytest.skip("precompiled")
 
     original = _rt.Sim.__init__
