@@ -103,3 +103,20 @@ def test_pipelined_gather_delivers_the_last_submitted_pass(world, tmp_path):
     got = np.load(out)
     base = np.arange(3 * 41, dtype=np.float64)
     assert np.array_equal(got["k1"], base * 2) and np.array_equal(got["k4"], base * 5)
+
+
+def test_seed_words_wrap_like_the_references_cl_int_arithmetic():
+    """CLODE::seedRNG(cl_int): `RNGstate[i] = mySeed + i` is 32-bit signed (wraps), then widened to 64 bits with sign extension
+    (clode/cpp/CLODE.cpp:447-453); the Python sharding helpers, the oracle helper and the C++ layer must agree near INT_MAX"""
+    from oracle.common import seed_states as oracle_seed_states
+
+    n = 10
+    seed = 2**31 - 4
+    got = sharding.seed_states_for(seed, n, np.arange(n))
+    want = oracle_seed_states(seed, n)
+    assert np.array_equal(got, want)
+    k = np.arange(2 * n, dtype=np.int64)
+    expect = ((seed + k + 2**31) % 2**32 - 2**31).astype(np.int64).astype(np.uint64)  # int32 wrap, sign extension
+    assert np.array_equal(got, expect)
+    assert got[3] == np.uint64(2**31 - 1) and got[4] == np.uint64(2**64 - 2**31)     # ... 0x7fffffff, then 0xffffffff80000000
+    assert np.array_equal(sharding.seed_states(seed, n, 2, 7), sharding.seed_states_for(seed, n, np.arange(2, 7)))
