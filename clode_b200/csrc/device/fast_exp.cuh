@@ -83,6 +83,7 @@ __device__ const double2 clode_exp2_table[128] = {
     {0x1.fa7c1819e90d8p+0, 0x1.74853f3a5931ep-55}, {0x1.fd3c22b8f71f1p+0, 0x1.2eb74966579e7p-57},
 };
 
+#if !defined(CLODE_EXP_2K)
 #ifndef CLODE_EXP_HOST_CHECK
 __shared__ double2 clode_exp2_smem[128];
 // every thread of the block, before any thread leaves the kernel
@@ -131,4 +132,90 @@ static __device__ __forceinline__ double clode_fast_exp(const double x)
     const int m1 = m >> 1;
     return y * __hiloint2double((1023 + m1) << 20, 0) * __hiloint2double((1023 + m - m1) << 20, 0);
 }
+
+#else // CLODE_EXP_2K ------------------------------------------------------------------------------------------------
+// The BRANCH-FREE variant (round 2).  In the version above every call ends in a branch around the rare cases, and a
+// branch is a scheduling barrier: the three sigmoids of a gating-variable right-hand side are evaluated one after the
+// other, each a ~20-deep dependent FP64 chain, which is what the low-occupancy kernels (C3 / C4 / C5: 16 warps per SM)
+// stall on (`wait` 40 %).  This one has no branch, so that — together with the branch-free reciprocal / division of
+// the PTX pass (rt/ptx_pass.hpp) — a right-hand side is ONE basic block and the chains interleave:
+//   * reduction by ln2/2048, 2^(j/2048) from a 16 KiB shared-memory table (one 8-byte word per entry), cubic
+//     polynomial r + r^2 (a + r/6) with a = 1/2 + R^2/24 (the Chebyshev economisation of the r^4/24 term on
+//     |r| <= R = ln2/4096): 8 FP64-pipe instructions instead of 11, error <= 1.1 ulp (table entry 0.5, final FMA 0.5,
+//     truncation 0.04; CUDA documents 1 ulp for its own exp, OpenCL C allows 3);
+//   * the scaling by 2^m as two factors ALWAYS, m = m1 + m2 with m1 = m >> 1: 2^m1 goes into the exponent field of the
+//     table entry (a normal number for every m: NaN-safe, unlike an exponent add on the result), 2^m2 is the one
+//     extra multiplication — it rounds only where the result is subnormal, zero or infinite, i.e. exactly the IEEE
+//     answer for every finite argument without a range test;
+//   * |x| >= 1024 and +-Inf (the low word of x * 2048/ln2 + 1.5 2^52 no longer holds an integer) are turned into
+//     p = 0, m = -+2044 by selects, which the same two factors scale to 0 / +Inf; a NaN flows through r, p and the
+//     final FMA untouched.
+// The table is built at kernel entry from the 128-entry hi/lo table above times 2^(i/2048), i < 16, in
+// double-double arithmetic (the rounded product differs from the correctly rounded entry in no case of the 2048:
+// tests/emu/fast_exp_check.cpp compares every entry with 80-bit arithmetic).
+__device__ const double2 clode_exp2_fine[16] = {
+    {0x1.0000000000000p+0, 0x0.0p+0}, {0x1.00162f3904052p+0, -0x1.7b5d0d58ea8f4p-58},
+    {0x1.002c605e2e8cfp+0, -0x1.d7c96f201bb2fp-55}, {0x1.0042936faa3d8p+0, -0x1.0484245243777p-55},
+    {0x1.0058c86da1c0ap+0, -0x1.5e00e62d6b30dp-56}, {0x1.006eff583fc3dp+0, -0x1.4acf197a00142p-54},
+    {0x1.0085382faef83p+0, 0x1.da93f90835f75p-56}, {0x1.009b72f41a12bp+0, 0x1.86364f8fbe8f8p-54},
+    {0x1.00b1afa5abcbfp+0, -0x1.4f6b2a7609f71p-55}, {0x1.00c7ee448ee02p+0, 0x1.4362ca5bc26f1p-56},
+    {0x1.00de2ed0ee0f5p+0, -0x1.406ac4e81a645p-57}, {0x1.00f4714af41d3p+0, -0x1.91b2060859321p-54},
+    {0x1.010ab5b2cbd11p+0, 0x1.c1d0660524e08p-54}, {0x1.0120fc089ff63p+0, 0x1.843aa8b9cbbc6p-55},
+    {0x1.0137444c9b5b5p+0, -0x1.2b6aeb6176892p-56}, {0x1.014d8e7ee8d2fp+0, 0x1.2edc08e5da99ap-56},
+};
+
+// 2^(j/2048) = 2^((j >> 4)/128) * 2^((j & 15)/2048), hi/lo product rounded once
+static __device__ __forceinline__ double clode_exp2k_entry(const unsigned int j)
+{
+    const double2 a = clode_exp2_table[j >> 4], b = clode_exp2_fine[j & 15u];
+    const double p = a.x * b.x;
+    const double e = fma(a.x, b.x, -p);
+    return p + fma(a.x, b.y, fma(a.y, b.x, e));
+}
+
+#ifndef CLODE_EXP_HOST_CHECK
+__shared__ double clode_exp2k_smem[2048];
+static __device__ __forceinline__ void clode_stage_exp_table()
+{
+    for (unsigned int j = threadIdx.x; j < 2048u; j += blockDim.x)
+        clode_exp2k_smem[j] = clode_exp2k_entry(j);
+    __syncthreads();
+}
+#define CLODE_EXP2K_ENTRY(j) clode_exp2k_smem[j]
+#else
+#define CLODE_EXP2K_ENTRY(j) clode_exp2k_entry(j)
+#endif
+
+__constant__ double clode_exp_c[6] = {
+    0x1.71547652b82fep+11,  // 2048 / ln2
+    0x1.8p52,               // 1.5 * 2^52: adding it leaves round(x * 2048/ln2) in the low word
+    -0x1.62e42fefa39efp-12, // -(ln2 / 2048), high part
+    -0x1.abc9e3b39803fp-67, // -(ln2 / 2048), low part
+    0x1.5555555555555p-3,   // 1/6
+    0x1.0000000a3fea0p-1};  // 1/2 + (ln2/4096)^2 / 24
+
+static __device__ __forceinline__ double clode_fast_exp(const double x)
+{
+    const double *c = clode_exp_c;
+    const double kf = fma(x, c[0], c[1]);
+    const int k = __double2loint(kf);
+    const double kd = kf - c[1];
+    double r = fma(kd, c[2], x);
+    r = fma(kd, c[3], r);
+    double p = fma(r * r, fma(r, c[4], c[5]), r);
+    const int hi = __double2hiint(x);
+    // 1024 <= |x| <= Inf, not NaN (a NaN has hi_abs > 0x7ff00000, or == with a non-zero low word: such a NaN cannot
+    // come out of an arithmetic instruction — the hardware quiets every NaN it produces)
+    const bool huge = (unsigned int)((hi & 0x7fffffff) - 0x40900000) <= (unsigned int)(0x7ff00000 - 0x40900000);
+    int m = k >> 11;
+    if (huge) { // selects
+        p = 0.0;
+        m = hi < 0 ? -2044 : 2044;
+    }
+    const int m1 = m >> 1;
+    const double t = CLODE_EXP2K_ENTRY(k & 2047);
+    const double ts = __hiloint2double(__double2hiint(t) + (m1 << 20), __double2loint(t)); // 2^(j/2048) 2^m1: normal
+    return fma(ts, p, ts) * __hiloint2double((1023 + m - m1) << 20, 0);
+}
+#endif // CLODE_EXP_2K
 #endif // CLODE_FAST_EXP_CUH

@@ -242,6 +242,7 @@ CLODE_DEV void mark_finished(const KernelArgs &a, const size_t i, const unsigned
 #if !CLODE_ADAPTIVE
 struct Controller {};
 CLODE_DEV Controller make_controller(const SolverParams &, realtype) { return Controller(); }
+CLODE_DEV realtype attempt_entry_step(const realtype dt, const SolverParams &) { return dt; }
 #endif
 
 CLODE_DEV bool advance(Instance &I, realtype &h, bool &clean, const SolverParams &sp, const Controller &ctl,
@@ -361,7 +362,7 @@ struct TransientJob {
     realtype h;
     bool clean;
     __device__ __forceinline__ TransientJob(const KernelArgs &a_) : a(a_), sp(solver_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) {}
-    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); step = 0; h = I.dt; clean = true; }
+    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); step = 0; h = attempt_entry_step(I.dt, sp); clean = true; }
     __device__ __forceinline__ bool live() const { return I.t <= t_end && step < sp.max_steps; }
     __device__ __forceinline__ void attempt() { if (advance(I, h, clean, sp, ctl, t_end)) ++step; }
     __device__ __forceinline__ void end(size_t i) { store_instance(I, a, i, step); }
@@ -606,7 +607,7 @@ struct WarmupJob {
     bool clean;
     __device__ __forceinline__ WarmupJob(const KernelArgs &a_)
         : a(a_), sp(solver_params(a_)), op(observer_params(a_)), ctl(make_controller(sp, (realtype)a_.t1)), t_end((realtype)a_.t1) CLODE_OBSERVER_INIT {}
-    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); ob.init(I); step = 0; h = I.dt; clean = true; }
+    __device__ __forceinline__ void begin(size_t i) { load_instance(I, a, i); ob.init(I); step = 0; h = attempt_entry_step(I.dt, sp); clean = true; }
     // strict '<' (initializeObserver.cl:62); one-pass observers do no warm-up integration at all
     __device__ __forceinline__ bool live() const { return CLODE_TWO_PASS && I.t < t_end && step < sp.max_steps; }
     __device__ __forceinline__ void attempt()
@@ -679,7 +680,7 @@ struct FeaturesJob {
         ObsLoad ld = {(const realtype *)a.od_real, a.od_uint, (size_t)a.n, i, 0, 0};
         ob.visit(ld);
         ob.open_means();
-        step = 0; h = I.dt; clean = true;
+        step = 0; h = attempt_entry_step(I.dt, sp); clean = true;
         alive = I.t <= t_end && step < sp.max_steps;
     }
     __device__ __forceinline__ bool live() const { return alive; }
@@ -847,7 +848,7 @@ struct TrajectoryJob {
         } else {
             resume_instance(I, a, i, step, row);
         }
-        h = I.dt;
+        h = attempt_entry_step(I.dt, sp);
     }
     // trajectory.cl:76; `row + 1 < row_end`: the next point still belongs to this launch's rows
     __device__ __forceinline__ bool unfinished() const { return I.t <= t_end && step < sp.max_steps && row < sp.max_store; }

@@ -216,6 +216,18 @@ CLODE_DEV void step_fixed(Instance &I)
 
 #else // CLODE_ADAPTIVE ---------------------------------------------------------------
 
+// The error estimate is h * (sum of e_i k_i) per variable, and the controller only uses its weighted maximum norm
+// max_j |err_j| / scale_j.  The effective step h is positive, so production double takes it out of the maximum — one
+// multiplication per attempt instead of one per variable (the norm moves by an ulp; the bit-exact tier and single
+// precision scale every component as the reference writes it, adaptive_bs23.clh:60, adaptive_dp45.clh:107).
+#if CLODE_EXACT_ARITH || CLODE_FAST_SINGLE
+#define CLODE_NORM_SCALED_ONCE 0
+#define CLODE_ERR_SCALE(h) (h) *
+#else
+#define CLODE_NORM_SCALED_ONCE 1
+#define CLODE_ERR_SCALE(h)
+#endif
+
 #if defined(EXPLICIT_BS23)
 #define ERR_ORDER RCONST(2.0)
 #define MAX_SHRINK RCONST(0.5)
@@ -249,7 +261,7 @@ CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, re
     getRHS(t1, xn, I.p, kn, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        err[j] = h * (c[5] * I.k1[j] + c[6] * k2[j] + c[7] * k3[j] + c[8] * kn[j]);
+        err[j] = CLODE_ERR_SCALE(h) (c[5] * I.k1[j] + c[6] * k2[j] + c[7] * k3[j] + c[8] * kn[j]);
     return h;
 }
 #else // EXPLICIT_DOPRI5
@@ -306,7 +318,7 @@ CLODE_DEV realtype trial_step(Instance &I, const realtype h_in, realtype &t1, re
     getRHS(t1, xn, I.p, kn, I.aux, I.w);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        err[j] = h * (c[E1] * k1[j] + c[E3] * k3[j] + c[E4] * k4[j] + c[E5] * k5[j] + c[E6] * k6[j] + c[E7] * kn[j]);
+        err[j] = CLODE_ERR_SCALE(h) (c[E1] * k1[j] + c[E3] * k3[j] + c[E4] * k4[j] + c[E5] * k5[j] + c[E6] * k6[j] + c[E7] * kn[j]);
     return h;
 }
 #endif
@@ -324,6 +336,7 @@ struct Controller {
     realtype reltol, floor_;
     realtype scale; // 0.8 * reltol^(1/(p+1))   (production double only)
     int floor_hi_min; // step_floor's exponent-field form applies to hi(t) in [floor_hi_min, 0x7ff00000): empty unless t_end > 0
+    int floor_hi_max; // production double: ... and 16 ulp(t) <= dtmax, i.e. hi(t) < floor_hi_max (adaptive_attempt)
 };
 #if CLODE_FAST_SINGLE
 #define CLODE_EXACT_CONTROLLER 0
@@ -371,8 +384,18 @@ CLODE_DEV Controller make_controller(const SolverParams &sp, const realtype t_en
     c.scale = RCONST(0.8) * pow(sp.reltol, RCONST(1.0) / (ERR_ORDER + RCONST(1.0)));
 #if defined(CLODE_SINGLE_PRECISION)
     c.floor_hi_min = t_end > ZERO ? (20 << 23) : 0x7f800000;
+    c.floor_hi_max = 0;
 #else
     c.floor_hi_min = t_end > ZERO ? (49 << 20) : 0x7ff00000;
+#if !CLODE_EXACT_ARITH
+    {   // 16 ulp(t) = 2^(E_t - 1071) <= 2^(E_dtmax - 1023) <= dtmax  <=>  E_t <= E_dtmax + 48
+        const int d_hi = __double2hiint((double)sp.dtmax);
+        const int top = (d_hi & 0x7ff00000) + (49 << 20);
+        c.floor_hi_max = (d_hi > 0 && d_hi < 0x7ff00000) ? (top < 0x7ff00000 ? top : 0x7ff00000) : 0;
+    }
+#else
+    c.floor_hi_max = 0;
+#endif
 #endif
     return c;
 }
@@ -417,6 +440,19 @@ CLODE_DEV realtype step_floor(const realtype t, const realtype t_end, const int 
 #endif
 }
 
+// The trial step an instance enters its first attempt with (the stored dt).  Production double keeps h <= dtmax as a
+// loop invariant so that the clamp at the top of an attempt is one compare; a NaN dt becomes 0, which that clamp raises
+// to hmin exactly as clamp(NaN, hmin, dtmax) does in the reference's fmin/fmax arithmetic.
+CLODE_DEV realtype attempt_entry_step(const realtype dt, const SolverParams &sp)
+{
+#if CLODE_EXACT_ARITH || CLODE_FAST_SINGLE
+    (void)sp;
+    return dt;
+#else
+    return dt == dt ? min_nn(dt, sp.dtmax) : ZERO;
+#endif
+}
+
 // One attempt of the step-size controller, adaptive_explicit_step.clh:9-81.
 // `h` is the trial step carried between attempts, `clean` is the reference's
 // noFailedSteps.  Returns true when the reference's stepper() would have returned
@@ -425,10 +461,31 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
                                  const realtype t_end)
 {
     const realtype floor_ = ctl.floor_;
-    const realtype hmin = step_floor(I.t, t_end, ctl.floor_hi_min);
     realtype t1, xn[NV], kn[NV], err[NV];
-
+    // hmin = 16 ulp(t), then h = clamp(h, hmin, dtmax) (adaptive_explicit_step.clh:17,31)
+#if CLODE_EXACT_ARITH || defined(CLODE_SINGLE_PRECISION)
+    const realtype hmin = step_floor(I.t, t_end, ctl.floor_hi_min);
     h = clamp_nn(h, hmin, sp.dtmax);
+#else
+    // Production double.  Common case (0 < t <= t_end, t normal, and 16 ulp(t) <= dtmax — folded into floor_hi_max): hmin
+    // is a power of two built from the exponent field of t (step_floor), its low word is zero, so `h < hmin` is a
+    // comparison of HIGH WORDS on the integer pipe; and h <= dtmax holds on entry (attempt_entry_step, the shrink of a
+    // rejected attempt, the clamp that ends an accepted one), so the clamp's upper bound cannot bind.  Same value as the
+    // two FP64 compares of the generic form, which every other case still takes.
+    realtype hmin;
+    {
+        const int t_hi = __double2hiint(I.t);
+        if (t_hi >= ctl.floor_hi_min && t_hi < ctl.floor_hi_max) {
+            const int f_hi = (t_hi & 0x7ff00000) - (48 << 20);
+            hmin = __hiloint2double(f_hi, 0);
+            if (__double2hiint(h) < f_hi) h = hmin;
+        } else {
+            hmin = step_floor(I.t, t_end, 0x7ff00000);
+            h = clamp_nn(h, hmin, sp.dtmax);
+        }
+    }
+#endif
+
     h = trial_step(I, h, t1, xn, kn, err);
 
     realtype nerr = opaque(ZERO);
@@ -438,17 +495,20 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
         err[j] = div_norm(err[j], max_nn(abs_nn(I.x[j]), max_nn(abs_nn(xn[j]), floor_)));
         nerr = max_nn(abs_nn(err[j]), nerr);
     }
+#if CLODE_NORM_SCALED_ONCE
+    nerr *= h; // h = t1 - t > 0 (hmin > 0): max_j |h s_j| / scale_j = h max_j |s_j| / scale_j
+#endif
     const bool reject = nerr > sp.reltol;
-    if (reject && h <= hmin) { // cannot shrink further: stepper() returns -1, state untouched
-        I.dt = hmin;
-        h = hmin;
-        clean = true;
-        return true;
-    }
     realtype factor = RCONST(0.5);
     if (clean)
         factor = controller_factor(ctl, nerr);
     if (reject) {
+        if (h <= hmin) { // cannot shrink further: stepper() returns -1, state untouched
+            I.dt = hmin;
+            h = hmin;
+            clean = true;
+            return true;
+        }
         h *= clean ? max_nn(factor, opaque(MAX_SHRINK)) : RCONST(0.5);
         clean = false;
         return false;

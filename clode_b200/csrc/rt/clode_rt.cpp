@@ -85,9 +85,21 @@ struct ProgramSpec {
     bool ext_smem_auto = false; // ... decided by clode_sim_build from the spill size of the features kernel
     bool library_exp = false; // keep CUDA's exp in production double builds (default: device/fast_exp.cuh)
     bool const_div = true; // ptx_pass.hpp: divisions by literal constants without the Newton refinement of the literal
+    bool branchless = false; // production double: branch-free exp (fast_exp.cuh, CLODE_EXP_2K) and rcp / div (ptx_pass.hpp)
     int block = 128, min_blocks = 4;
     int kernel_min_blocks[4] = {0, 0, 0, 0}; // transient, initializeObserver, features, trajectory; 0 = min_blocks
 };
+
+// Branch-free exp / reciprocal / division in production double builds (DESIGN.md §3 "One basic block per right-hand
+// side"): CLODE_BRANCHLESS=0|1 overrides the default.
+bool branchless_default()
+{
+    if (const char *env = std::getenv("CLODE_BRANCHLESS")) {
+        if (*env == '0') return false;
+        if (*env == '1') return true;
+    }
+    return false;
+}
 
 int parse_desc(const clode_program_desc *d, ProgramSpec &s)
 {
@@ -111,6 +123,7 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.work_queue = d->work_queue != 0;
     s.const_div = !s.bit_exact && d->ieee_constant_division == 0;
     s.library_exp = d->library_exp != 0;
+    s.branchless = s.const_div && !s.single && branchless_default();
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     {
@@ -157,6 +170,7 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.kernels & CLODE_KERNEL_TRAJECTORY) o.push_back("-DCLODE_WITH_TRAJECTORY");
     if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
     if (s.library_exp) o.push_back("-DCLODE_LIBRARY_EXP");
+    if (s.branchless && !s.library_exp) o.push_back("-DCLODE_EXP_2K");
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
@@ -327,6 +341,7 @@ int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &lo
     std::string key_src = full_source(s);
     if (s.const_div) key_src += ptxas_shim() ? "// ptx pass v2, assembled by libclode_ptxas\n" : "// ptx pass v2, assembled by nvJitLink\n";
     if (s.const_div && hoist_literals(s)) key_src += "// double literals through the constant bank\n";
+    if (s.branchless) key_src += "// branch-free rcp / div v1\n";
     uint64_t h1 = fnv1a(key_src, 1469598103934665603ull), h2 = fnv1a(key_src, 0x9e3779b97f4a7c15ull);
     char name[64];
     std::snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
@@ -382,8 +397,9 @@ int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &lo
         rtc->nvrtcGetPTX(prog, &ptx[0]);
         rtc->nvrtcDestroyProgram(&prog);
         while (!ptx.empty() && ptx.back() == '\0') ptx.pop_back();
-        int replaced = 0, hoisted = 0;
+        int replaced = 0, hoisted = 0, rcps = 0, divs = 0;
         ptx = rewrite_constant_divisions(ptx, &replaced);
+        if (s.branchless) ptx = rewrite_variable_divisions(ptx, &rcps, &divs);
         if (hoist_literals(s)) ptx = hoist_f64_immediates(ptx, &hoisted);
         if (const char *dump = std::getenv("CLODE_DUMP_PTX")) { // development aid: the PTX as it goes to ptxas
             std::ofstream f(dump);
@@ -392,7 +408,8 @@ int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &lo
         int rc = assemble_ptx(ptx, cubin, log);
         if (rc) return rc;
         log += "\n(ptx pass: " + std::to_string(replaced) + " divisions by a literal constant rewritten, " + std::to_string(hoisted) +
-               " double literals moved to the constant bank)";
+               " double literals moved to the constant bank, " + std::to_string(rcps) + " reciprocals and " + std::to_string(divs) +
+               " divisions made branch-free)";
     } else {
         r = rtc->nvrtcGetCUBINSize(prog, &size);
         if (r != NVRTC_SUCCESS || size == 0) {
