@@ -332,9 +332,9 @@ CLODE_DEV void quadraticInterpVertex(realtype t[], realtype y[], realtype *tv, r
     !defined(CLODE_LIBRARY_EXP) && !defined(__CUDACC_EMU__)
 #include "fast_exp.cuh"
 #define exp(x) clode_fast_exp(x)
-#define CLODE_KERNEL_PROLOGUE() clode_stage_exp_table()
+#define CLODE_HAVE_FAST_EXP 1
 #else
-#define CLODE_KERNEL_PROLOGUE()
+#define CLODE_HAVE_FAST_EXP 0
 #endif
 
 #endif // CLODE_CL_COMPAT_CUH

@@ -40,6 +40,19 @@
 #define CLODE_MIN_BLOCKS_TRAJECTORY CLODE_MIN_BLOCKS
 #endif
 
+// Every kernel starts by staging the tables of the production-double math (exp: cl_compat.cuh / fast_exp.cuh; the polar
+// method's logarithm: rng.cuh / fast_polar.cuh) in shared memory; all threads of the block, before any of them returns.
+CLODE_DEV void clode_kernel_prologue()
+{
+#if CLODE_HAVE_FAST_EXP
+    clode_stage_exp_table();
+#endif
+#if CLODE_HAVE_FAST_POLAR
+    clode_stage_polar_table();
+#endif
+}
+#define CLODE_KERNEL_PROLOGUE() clode_kernel_prologue()
+
 // Launch arguments: one struct in __constant__ memory (`clode_args`), written by the host
 // with an in-stream copy before each launch; every field is a warp-uniform constant-bank load.
 // NOTE: deliberately NOT a by-value kernel parameter.  With a by-value struct larger than

@@ -10,6 +10,15 @@
 #ifndef CLODE_RNG_CUH
 #define CLODE_RNG_CUH
 
+// production double builds of the stochastic stepper: the polar method's scale factor from fast_polar.cuh
+#if defined(CLODE_FAST_POLAR) && defined(STOCHASTIC_EULER) && defined(CLODE_DOUBLE_PRECISION) && !defined(CLODE_BITEXACT) && \
+    !defined(CLODE_REFERENCE_MATH) && !defined(__CUDACC_EMU__)
+#include "fast_polar.cuh"
+#define CLODE_HAVE_FAST_POLAR 1
+#else
+#define CLODE_HAVE_FAST_POLAR 0
+#endif
+
 struct RngStream {
     unsigned long long s0, s1;
     realtype spare;
@@ -56,7 +65,11 @@ CLODE_DEV realtype rng_normal(RngStream &g)
         b = rng_add(rng_mul(RCONST(2.0), rng_uniform(g)), -ONE);
         q = rng_add(rng_mul(a, a), rng_mul(b, b));
     } while (q >= ONE);
+#if CLODE_HAVE_FAST_POLAR
+    q = clode_polar_scale(q);
+#else
     q = sqrt(rng_mul(-RCONST(2.0), log(q)) / q);
+#endif
     g.spare = rng_mul(b, q);
     g.have_spare = true;
     return rng_mul(a, q);

@@ -493,6 +493,15 @@ CLODE_DEV bool adaptive_attempt(Instance &I, realtype &h, bool &clean, const Sol
     for (int j = 0; j < NV; ++j) {
         // fmax(fmax(|x|, |xn|), floor) and norm_inf's fmax(|e|, running), NaN operands ignored as in the reference
         err[j] = div_norm(err[j], max_nn(abs_nn(I.x[j]), max_nn(abs_nn(xn[j]), floor_)));
+#if !CLODE_EXACT_ARITH && !defined(CLODE_SINGLE_PRECISION)
+        if (j == 0) {
+            // fmax(|e|, 0) only drops a NaN: a test of the high word (|e| has no sign; every NaN an arithmetic instruction
+            // produces is quiet, high word > 0x7ff00000) on the integer pipe instead of an FP64 compare
+            const double e0 = abs_nn(err[0]);
+            nerr = __double2hiint(e0) <= 0x7ff00000 ? e0 : 0.0;
+            continue;
+        }
+#endif
         nerr = max_nn(abs_nn(err[j]), nerr);
     }
 #if CLODE_NORM_SCALED_ONCE

@@ -86,6 +86,7 @@ struct ProgramSpec {
     bool library_exp = false; // keep CUDA's exp in production double builds (default: device/fast_exp.cuh)
     bool const_div = true; // ptx_pass.hpp: divisions by literal constants without the Newton refinement of the literal
     bool branchless = false; // production double: branch-free exp (fast_exp.cuh, CLODE_EXP_2K) and rcp / div (ptx_pass.hpp)
+    bool fast_polar = false; // production double, stochastic stepper: sqrt(-2 log q / q) from device/fast_polar.cuh
     int block = 128, min_blocks = 4;
     int kernel_min_blocks[4] = {0, 0, 0, 0}; // transient, initializeObserver, features, trajectory; 0 = min_blocks
 };
@@ -95,6 +96,16 @@ struct ProgramSpec {
 bool branchless_default()
 {
     if (const char *env = std::getenv("CLODE_BRANCHLESS")) {
+        if (*env == '0') return false;
+        if (*env == '1') return true;
+    }
+    return true; // profiles/r02_branchless_sweep.log: C3 548 -> 482 ms, C4 694 -> 644, C5 rk4 15.5 -> 13.8, C5 dopri5 14.4 -> 12.0
+}
+
+// The polar method's scale factor by table log + one rsqrt correction (device/fast_polar.cuh): CLODE_FAST_POLAR=0|1.
+bool fast_polar_default()
+{
+    if (const char *env = std::getenv("CLODE_FAST_POLAR")) {
         if (*env == '0') return false;
         if (*env == '1') return true;
     }
@@ -124,6 +135,7 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.const_div = !s.bit_exact && d->ieee_constant_division == 0;
     s.library_exp = d->library_exp != 0;
     s.branchless = s.const_div && !s.single && branchless_default();
+    s.fast_polar = !s.bit_exact && !s.single && s.stepper == find_name(kStepperNames, 6, "seuler") && fast_polar_default();
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     {
@@ -171,6 +183,7 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.bit_exact) o.push_back("-DCLODE_BITEXACT");
     if (s.library_exp) o.push_back("-DCLODE_LIBRARY_EXP");
     if (s.branchless && !s.library_exp) o.push_back("-DCLODE_EXP_2K");
+    if (s.fast_polar) o.push_back("-DCLODE_FAST_POLAR");
     if (s.work_queue) o.push_back("-DCLODE_WORK_QUEUE");
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
@@ -332,7 +345,11 @@ bool hoist_literals(const ProgramSpec &s)
         if (*env == '0') return false;
         if (*env == '1') return true;
     }
-    return !(s.kernels & CLODE_KERNEL_FEATURES);
+    // With the branch-free right-hand side (one basic block) the fixed-step features kernel gains as well (C4 644 -> 623 ms);
+    // the adaptive features kernels do not (C3 482 -> 509 ms: 128 registers + spills, the constant operands cost more than
+    // the uniform-datapath moves they replace)   (profiles/r02_branchless_sweep.log)
+    const bool adaptive = s.stepper == 3 || s.stepper == 4; // bs23, dopri5 (kStepperNames)
+    return !(s.kernels & CLODE_KERNEL_FEATURES) || (s.branchless && !adaptive);
 }
 
 int compile_spec(const ProgramSpec &s, std::vector<char> &cubin, std::string &log)
