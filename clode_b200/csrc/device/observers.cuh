@@ -861,9 +861,11 @@ struct Observer {
     __device__ __forceinline__ bool event(const Instance &I, const ObserverParams &op)
     {
         if (steps < 2) return false;
-        if (g_xmax - g_xmin < op.minXamp) return false;
         if (up) return false;
-        return I.x[E_VAR_IX] > x_up && I.k1[E_VAR_IX] > dx_up;
+        if (!(I.x[E_VAR_IX] > x_up && I.k1[E_VAR_IX] > dx_up)) return false;
+        // the amplitude test (observer_threshold_2.clh:331) last: it only decides at an upward crossing, where the
+        // reference evaluates it first — same result, two FP64 instructions fewer on every other step
+        return !(g_xmax - g_xmin < op.minXamp);
     }
     __device__ __forceinline__ bool on_event(const Instance &I, const ObserverParams &op)
     {

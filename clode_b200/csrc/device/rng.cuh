@@ -52,6 +52,16 @@ CLODE_DEV realtype rng_uniform(RngStream &g)
     return rng_mul(rng_from_u64(rng_next(g)), RCONST(5.421010862427522e-20));
 }
 
+// 2 * uniform - 1 (clODE_random.cl:100-101).  The two scalings of the converted integer, by 2^-64 and by 2, are exact
+// (powers of two; no underflow: the smallest non-zero value is 2^-64), so RN(RN(RN(u) 2^-64) 2 - 1) = RN(RN(u) 2^-63 - 1):
+// ONE fused multiply-add gives the reference's value bit for bit in every tier, instead of two multiplications and an
+// addition (2 of the ~150 FP64-pipe instructions of a C4 step, per candidate).
+#if defined(CLODE_SINGLE_PRECISION)
+CLODE_DEV realtype rng_symmetric(RngStream &g) { return __fmaf_rn(rng_from_u64(rng_next(g)), 1.0842021724855044e-19f, -ONE); }
+#else
+CLODE_DEV realtype rng_symmetric(RngStream &g) { return __fma_rn(rng_from_u64(rng_next(g)), 1.0842021724855044e-19, -ONE); }
+#endif
+
 // N(0,1) by the Marsaglia polar method; the second variate of each pair is kept
 CLODE_DEV realtype rng_normal(RngStream &g)
 {
@@ -61,8 +71,8 @@ CLODE_DEV realtype rng_normal(RngStream &g)
     }
     realtype a, b, q;
     do {
-        a = rng_add(rng_mul(RCONST(2.0), rng_uniform(g)), -ONE);
-        b = rng_add(rng_mul(RCONST(2.0), rng_uniform(g)), -ONE);
+        a = rng_symmetric(g);
+        b = rng_symmetric(g);
         q = rng_add(rng_mul(a, a), rng_mul(b, b));
     } while (q >= ONE);
 #if CLODE_HAVE_FAST_POLAR

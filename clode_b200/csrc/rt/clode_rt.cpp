@@ -109,7 +109,7 @@ bool fast_polar_default()
         if (*env == '0') return false;
         if (*env == '1') return true;
     }
-    return false;
+    return true; // C4 622.9 -> 591.7 ms (profiles/r02_branchless_sweep.log)
 }
 
 int parse_desc(const clode_program_desc *d, ProgramSpec &s)

@@ -31,6 +31,8 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline double __ull2double_rn(unsigned long long u) { return (double)u; }
 static inline float __ull2float_rn(unsigned long long u) { return (float)u; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
