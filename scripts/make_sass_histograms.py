@@ -31,7 +31,10 @@ def main():
         for tag, model, stepper, obs, kern, kname, m, kw in cases:
             nv, npar, na, nw = MODELS[model]
             prog = _rt.Program(rhs_source(model), stepper, nv, npar, na, nw, observer=obs, kernels=kern, min_blocks_per_sm=m, **kw)
+            if obs == "thresh2":  # what clode_sim_build decides on the GPU for this program: observer extents in shared memory
+                os.environ["CLODE_EXT_SMEM"] = "1"
             cubin, _ = _rt.compile_program(prog)
+            os.environ.pop("CLODE_EXT_SMEM", None)
             with tempfile.NamedTemporaryFile(suffix=".cubin", delete=False) as f:
                 f.write(cubin)
             res = subprocess.run(["cuobjdump", "--dump-resource-usage", f.name], capture_output=True, text=True).stdout.splitlines()
