@@ -121,3 +121,33 @@ def test_step_floor_exponent_identity():
     assert np.all((hi >= (49 << 20)) & (hi < 0x7FF00000))
     got = (((hi & 0x7FF00000) - (48 << 20)).astype(np.uint64) << np.uint64(32)).view(np.float64)
     assert np.array_equal(got, want)
+
+
+def test_attempt_clamp_on_high_words_identity():
+    """steppers.cuh adaptive_attempt(), production double: with hmin = 16 ulp(t) = {hi', 0} (a power of two, zero low word),
+    h <= dtmax (loop invariant) and hi(t) < floor_hi_max (which encodes 16 ulp(t) <= dtmax),
+        clamp(h, hmin, dtmax) = fmin(fmax(h, hmin), dtmax)   (adaptive_explicit_step.clh:31)
+    equals  `hi(h) < hi' ? hmin : h`  — an integer comparison of high words."""
+    rng = np.random.default_rng(21)
+    n = 200000
+    t = np.exp(rng.uniform(np.log(1e-6), np.log(1e12), n))
+    dtmax = np.exp(rng.uniform(np.log(1e-9), np.log(1e6), n))
+    # h anywhere from far below hmin to dtmax, negative and zero values included; a share sits within a few ulp of hmin
+    hi_t = (t.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    f_hi = (hi_t & 0x7FF00000) - (48 << 20)
+    hmin = (f_hi.astype(np.uint64) << np.uint64(32)).view(np.float64)
+    h = np.minimum(np.exp(rng.uniform(np.log(1e-30), np.log(1e6), n)), dtmax)
+    near = rng.random(n) < 0.3
+    h[near] = np.minimum((hmin * (1.0 + rng.integers(-4, 5, n) * 2.0 ** -52))[near], dtmax[near])
+    h[rng.random(n) < 0.02] = 0.0
+    h[rng.random(n) < 0.02] *= -1.0
+    d_hi = (dtmax.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    floor_hi_max = np.minimum(0x7FF00000, (d_hi & 0x7FF00000) + (49 << 20))
+    fast = (hi_t >= (49 << 20)) & (hi_t < floor_hi_max)
+    assert fast.mean() > 0.5 and (~fast).sum() > 100      # both sides of the 16 ulp(t) <= dtmax condition are sampled
+    assert np.all(hmin[fast] <= dtmax[fast])
+    want = np.minimum(np.maximum(h, hmin), dtmax)
+    hi_h = (h.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    hi_h = np.where(hi_h >= 1 << 31, hi_h - (1 << 32), hi_h)  # as the signed 32-bit word the device compares
+    got = np.where(hi_h < f_hi, hmin, h)
+    assert np.array_equal(got[fast], want[fast])
