@@ -93,11 +93,17 @@ typedef struct clode_program_desc {
                                  evaluated as q = x*y, q + (x - c*q)*y with y = RN(1/c) from the host — the
                                  correctly rounded quotient for |x| in [2^-511, 2^512), one ulp outside —
                                  instead of ptxas' generic sequence, which Newton-refines the literal's
-                                 reciprocal at run time; 1: leave every division to ptxas              */
-    int library_exp;          /* 0 (default): in production double builds exp() is the engine's table + degree-5
-                                 polynomial (device/fast_exp.cuh, <= 0.52 ulp, 11 FP64 instructions); 1: CUDA's
-                                 libdevice exp (1 ulp, 15 FP64 instructions + coefficient moves).  Ignored by
-                                 bit_exact and single-precision builds                                      */
+                                 reciprocal at run time; and (double precision) `1 / x`, `a / x` with a variable x
+                                 are ptxas' own fast-path sequence with selects instead of the branch to its
+                                 slow path (bit-identical to IEEE for normal operands and results, zeros,
+                                 infinities and NaNs; subnormal or >= 2^1022 divisors are flushed; environment
+                                 CLODE_BRANCHLESS=0 keeps ptxas' expansion); 1: leave every division to ptxas */
+    int library_exp;          /* 0 (default): in production double builds exp() is the engine's table + polynomial
+                                 (device/fast_exp.cuh: branch-free, 2048-entry table + cubic, <= 1.06 ulp, 9 FP64
+                                 instructions; with CLODE_BRANCHLESS=0 the 128-entry hi/lo table + degree 5,
+                                 <= 0.52 ulp, 11 instructions and a branch); 1: CUDA's libdevice exp (1 ulp,
+                                 15 FP64 instructions + coefficient moves).  Ignored by bit_exact and
+                                 single-precision builds                                                    */
 } clode_program_desc;
 
 /* compile only (no GPU needed): returns malloc'd cubin + log; caller frees with clode_free */
