@@ -130,6 +130,10 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     if (s.n_store < 0) return fail(CLODE_ERR_INVALID, "n_store_events must be >= 0");
     s.kernels = d->kernels | CLODE_KERNEL_TRANSIENT;
     s.bit_exact = d->bit_exact != 0;
+    // CLODE_BIT_EXACT=1: the bit-exact tier for callers that cannot set the field — the C++ classes and the Python front
+    // end build their programs without it (double precision only; a single-precision program stays as it is)
+    if (const char *env = std::getenv("CLODE_BIT_EXACT"))
+        if (*env == '1' && !s.single) s.bit_exact = true;
     if (s.bit_exact && s.single) return fail(CLODE_ERR_INVALID, "bit_exact requires double precision");
     s.work_queue = d->work_queue != 0;
     s.const_div = !s.bit_exact && d->ieee_constant_division == 0;

@@ -111,3 +111,23 @@ def test_build_errors_are_reported_with_the_compiler_log(rt):
     assert e.value.code == 1 and "unknown stepper" in str(e.value)
     with pytest.raises(rt.RtError):
         rt.compile_program(rt.Program("", "rk4", 2, 1, observer="thresh2", f_var_ix=5))
+
+
+def test_bit_exact_tier_can_be_forced_from_the_environment(monkeypatch):
+    """CLODE_BIT_EXACT=1: programs built without the bit_exact field (the C++ classes, the Python front end) get the
+    bit-exact tier — no contraction, portable math, no PTX pass; single-precision programs are left alone"""
+    from clode_b200 import _rt
+    from clode_b200.models import MODELS, rhs_source
+
+    nv, npar, na, nw = MODELS["lactotroph"]
+    prog = _rt.Program(rhs_source("lactotroph"), "bs23", nv, npar, na, nw, observer="thresh2", kernels=_rt.KERNEL_FEATURES, min_blocks_per_sm=4)
+    assert "-DCLODE_BITEXACT" not in _rt.program_source(prog).splitlines()[0]
+    monkeypatch.setenv("CLODE_BIT_EXACT", "1")
+    head = _rt.program_source(prog).splitlines()[0]
+    assert "-DCLODE_BITEXACT" in head and "--fmad=false" in head and "-DCLODE_EXP_2K" not in head
+    cubin, log = _rt.compile_program(prog)
+    assert cubin[:4] == b"\x7fELF" and "ptx pass" not in log
+    import dataclasses
+
+    single = _rt.program_source(dataclasses.replace(prog, single_precision=True)).splitlines()[0]
+    assert "-DCLODE_BITEXACT" not in single
