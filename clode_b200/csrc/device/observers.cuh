@@ -139,7 +139,7 @@ CLODE_DEV realtype pick3(const realtype v[3], int at) { return at == 0 ? v[0] : 
 // in registers they cost the fat observers 46 registers (nVar = 4) that the trial step then has to spill around:
 // C3's features kernel executed 72 local loads + 51 local stores per attempt before this.  The accesses are volatile
 // so that the compiler does not promote the words back into registers for the whole time loop.
-#if defined(CLODE_EXT_SMEM) && !defined(CLODE_OBS_SMEM) && !defined(__CUDACC_EMU__)
+#if defined(CLODE_EXT_SMEM) && !defined(CLODE_OBS_SMEM) && (!defined(__CUDACC_EMU__) || defined(CLODE_EMU_EXT_SMEM))
 #define CLODE_EXT_IN_SMEM 1
 // thresh2 additionally keeps its four Schmitt-trigger thresholds there: written once when the observer is armed,
 // read (two of them) on every accepted step of the features pass
@@ -185,6 +185,34 @@ struct Extents {
     // time-weighted means (all observers except nhood1)
     __device__ __forceinline__ void update_time(const Instance &I, const MeanWeight &w)
     {
+#if CLODE_EXT_IN_SMEM && defined(CLODE_EXT_BATCH)
+        // Default since the end of round 2 (CLODE_EXT_BATCH=0 turns it off; enabled after the last GPU measurement of the round,
+        // so its effect is NOT in the measured numbers — its results are checked bit for bit on the emulated device code,
+        // tests/test_device_emu.py::test_extents_in_shared_memory_placement_matches_oracle): the volatile accesses keep the
+        // words out of registers, but they also pin every load right before its use — the ncu source page of C3's features
+        // launch shows 28 exposed shared-memory round trips per accepted step, a fifth of the launch's stall samples
+        // (profiles/r02b_c3_features_source_hotspots.txt).  Here the words of a variable are loaded first (independent
+        // LDS, in flight together), then compared / accumulated and stored exactly as below: same values, same stores.
+        // One variable at a time — five loads in flight, four predicates live (a batch over all variables makes ptxas
+        // spill predicates into a general register, ~50 LOP3 per step).
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const realtype c0 = xmax[j], c1 = xmin[j], c2 = xmean[j], c3 = dxmax[j], c4 = dxmin[j];
+            if (I.x[j] > c0) xmax[j] = I.x[j];
+            if (I.x[j] < c1) xmin[j] = I.x[j];
+            xmean[j] = mean_time(c2, I.x[j], w);
+            if (I.k1[j] > c3) dxmax[j] = I.k1[j];
+            if (I.k1[j] < c4) dxmin[j] = I.k1[j];
+        }
+#pragma unroll
+        for (int j = 0; j < N_AUX; ++j) {
+            const realtype c0 = amax[j], c1 = amin[j], c2 = amean[j];
+            if (I.aux[j] > c0) amax[j] = I.aux[j];
+            if (I.aux[j] < c1) amin[j] = I.aux[j];
+            amean[j] = mean_time(c2, I.aux[j], w);
+        }
+        return;
+#endif
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             ext_max(xmax[j], I.x[j]);

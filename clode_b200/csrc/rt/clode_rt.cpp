@@ -112,6 +112,19 @@ bool fast_polar_default()
     return true; // C4 622.9 -> 591.7 ms (profiles/r02_branchless_sweep.log)
 }
 
+// Static shared memory of a program's kernels with the observer extents placed there (observers.cuh `clode_ext_smem`:
+// 5 nVar + 3 max(nAux, 1) rows, + 4 for thresh2's thresholds, of one real per thread) next to the tables the production
+// double math stages (fast_exp.cuh: 16 KiB branch-free / 2 KiB; fast_polar.cuh: 6 KiB): must stay within 48 KiB.
+bool ext_smem_fits(const ProgramSpec &s)
+{
+    const size_t rows = 5 * (size_t)s.n_var + 3 * (size_t)std::max(s.n_aux, 1) + (s.observer == 5 ? 4 : 0);
+    size_t bytes = rows * (size_t)s.block * (s.single ? 4 : 8);
+    const bool fast_exp = !s.single && !s.bit_exact && !s.library_exp;
+    if (fast_exp) bytes += s.branchless ? 2048 * 8 : 128 * 16;
+    if (s.fast_polar) bytes += 256 * 24;
+    return bytes + 1024 <= 48 * 1024; // 1 KiB of slack: alignment, the staged-trajectory path never combines with a features kernel
+}
+
 int parse_desc(const clode_program_desc *d, ProgramSpec &s)
 {
     if (!d || !d->rhs_source) return fail(CLODE_ERR_INVALID, "program description or rhs_source is null");
@@ -142,16 +155,17 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.fast_polar = !s.bit_exact && !s.single && s.stepper == find_name(kStepperNames, 6, "seuler") && fast_polar_default();
     s.staged = d->staged_trajectory != 0;
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
+    s.block = d->block_size > 0 ? d->block_size : 128;
+    if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
     {
         // extents of the multi-variable observers in shared memory: forced by CLODE_EXT_SMEM=1, forbidden by =0, otherwise
-        // decided at build time from the features kernel's spill size (clode_sim_build)
+        // decided at build time from the features kernel's spill size (clode_sim_build) — if the array fits beside the
+        // tables of the production math in the 48 KiB of static shared memory a kernel may declare
         const char *env = std::getenv("CLODE_EXT_SMEM");
-        const bool possible = (s.kernels & CLODE_KERNEL_FEATURES) && s.observer != 0 && !s.obs_smem;
+        const bool possible = (s.kernels & CLODE_KERNEL_FEATURES) && s.observer != 0 && !s.obs_smem && ext_smem_fits(s);
         s.ext_smem = env && *env == '1' && possible;
         s.ext_smem_auto = !(env && (*env == '0' || *env == '1')) && possible;
     }
-    s.block = d->block_size > 0 ? d->block_size : 128;
-    if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
     s.min_blocks = d->min_blocks_per_sm > 0 ? d->min_blocks_per_sm : 4; // 0 = chosen at build time (clode_sim_build)
     return CLODE_OK;
 }
@@ -192,6 +206,12 @@ std::vector<std::string> compile_options(const ProgramSpec &s)
     if (s.staged) o.push_back("-DCLODE_TRAJ_STAGED");
     if (s.obs_smem) o.push_back("-DCLODE_OBS_SMEM");
     if (s.ext_smem) o.push_back("-DCLODE_EXT_SMEM");
+    if (s.ext_smem) {
+        // the shared-memory extents of one variable are loaded together before they are compared (observers.cuh); CLODE_EXT_BATCH=0
+        // restores the load-compare-store chain per word
+        const char *env = std::getenv("CLODE_EXT_BATCH");
+        if (!(env && *env == '0')) o.push_back("-DCLODE_EXT_BATCH");
+    }
     if (const char *extra = std::getenv("CLODE_EXTRA_DEFINES")) { // development knob: space-separated -D options (A/B sweeps)
         std::istringstream is(extra);
         std::string tok;

@@ -14,6 +14,7 @@
 #define __grid_constant__
 #define __constant__
 #define __restrict__
+#define __shared__ static thread_local   /* one host thread runs the threads of a block one after the other */
 
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local emu_dim3 blockIdx, blockDim, threadIdx, gridDim;

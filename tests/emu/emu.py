@@ -50,7 +50,7 @@ def _ptr(a):
 
 
 class EmuLib:
-    def __init__(self, cfg: Config, f_var_ix=0, e_var_ix=0):
+    def __init__(self, cfg: Config, f_var_ix=0, e_var_ix=0, extra_defs=()):
         self.cfg = cfg
         self.n_var, self.n_par, self.n_aux, self.n_wiener = cfg.shape
         self.real = cfg.real
@@ -61,6 +61,7 @@ class EmuLib:
             f"-DN_STORE_EVENTS={cfg.n_store_events}", f"-DF_VAR_IX={f_var_ix}", f"-DE_VAR_IX={e_var_ix}",
             "-DCLODE_WITH_FEATURES", "-DCLODE_WITH_TRAJECTORY", f'-DEMU_RHS_FILE="{cfg.rhs_file}"',
         ]
+        defs += list(extra_defs)  # e.g. the shared-memory placement of the observer extents (observers.cuh)
         if cfg.math == "pm":
             defs.append("-DCLODE_BITEXACT")
         else:
@@ -70,7 +71,7 @@ class EmuLib:
             h.update(open(os.path.join(DEVICE, f), "rb").read())
         h.update(open(cfg.rhs_file, "rb").read())
         os.makedirs(BUILD, exist_ok=True)
-        so = os.path.join(BUILD, f"emu_{cfg.tag}_{h.hexdigest()[:10]}.so")
+        so = os.path.join(BUILD, f"emu_{cfg.tag}_{h.hexdigest()[:10]}.so")  # the digest covers extra_defs
         if not os.path.exists(so):
             cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", f"-ffp-contract={cfg.contract}", "-fno-math-errno",
                    "-fPIC", "-shared", "-w", f"-I{HERE}", f"-I{DEVICE}", *defs,

@@ -180,3 +180,27 @@ def test_scheduled_time_loop_handles_max_steps_and_empty_rounds():
     got.pop("launches")
     assert_bit_equal(got, want, "max_steps cut-off")
     assert got["steps"].max() == 333
+
+
+@pytest.mark.parametrize("observer", ["basicall", "localmax", "nhood2", "thresh2"])
+@pytest.mark.parametrize("batch", [False, True])
+def test_extents_in_shared_memory_placement_matches_oracle(observer, batch):
+    """observers.cuh, CLODE_EXT_SMEM: the extents / means of the multi-variable observers (and thresh2's thresholds) in a
+    shared-memory array instead of registers — what the runtime selects for features kernels that spill (C3) — and its
+    opt-in variant that loads all words before it compares (CLODE_EXT_BATCH): both bit-identical to the oracle.  The
+    emulation runs the threads of a block one after the other, so `__shared__` is a per-host-thread static array."""
+    ns = 2 if observer in ("localmax", "nhood2", "thresh2") else 0
+    n = 7
+    ts, x0, pars = ensemble("lactotroph", n)
+    ts = (ts[0], ts[1] / 5)
+    sp = Solver(dt=0.1, dtmax=10.0, abstol=1e-6, reltol=1e-4, max_steps=100000, max_store=90, nout=7)
+    op = Observer(max_event_count=30, max_event_timestamps=ns, x_up_threshold=0.3, x_down_threshold=0.2, nhood_radius=0.1)
+    cfg = Config("lactotroph", "bs23", observer, ns, math="pm")
+    defs = ("-DCLODE_EXT_SMEM", "-DCLODE_EMU_EXT_SMEM", "-DCLODE_BLOCK=128") + (("-DCLODE_EXT_BATCH",) if batch else ())
+    A, B = EmuLib(cfg, extra_defs=defs), restate.OracleLib(cfg)
+    got, want = run_oracle(A, "features", ts, x0, pars, sp, op), run_oracle(B, "features", ts, x0, pars, sp, op)
+    assert_bit_equal(got, want, cfg.tag + (" batched" if batch else " in shared memory"))
+    # and a continued call (the record travels through the persistent layout in between)
+    r2a = A.features((ts[1], 2 * ts[1]), got["xf"], pars, sp, op, got["dt"], got["rng"], initialize=False)
+    r2b = B.features((ts[1], 2 * ts[1]), want["xf"], pars, sp, op, want["dt"], want["rng"], initialize=False)
+    assert_bit_equal(r2a, r2b, cfg.tag + " continued")

@@ -131,3 +131,30 @@ def test_bit_exact_tier_can_be_forced_from_the_environment(monkeypatch):
 
     single = _rt.program_source(dataclasses.replace(prog, single_precision=True)).splitlines()[0]
     assert "-DCLODE_BITEXACT" not in single
+
+
+def test_extents_go_to_shared_memory_only_when_the_array_fits(monkeypatch):
+    """the observer extents in shared memory (CLODE_EXT_SMEM, observers.cuh) share the 48 KiB of static shared memory with
+    the tables of the production math (16 KiB exp, 6 KiB polar method): a program for which the sum does not fit keeps the
+    extents in registers instead of failing in ptxas; where it fits, one variable's words are loaded together (CLODE_EXT_BATCH)"""
+    from clode_b200 import _rt
+    from clode_b200.models import MODELS, rhs_source
+
+    monkeypatch.setenv("CLODE_EXT_SMEM", "1")
+
+    def head(model, stepper, observer, **kw):
+        nv, npar, na, nw = MODELS[model]
+        prog = _rt.Program(rhs_source(model), stepper, nv, npar, na, nw, observer=observer, kernels=_rt.KERNEL_FEATURES, min_blocks_per_sm=4, **kw)
+        cubin, _ = _rt.compile_program(prog)
+        assert cubin[:4] == b"\x7fELF"
+        return _rt.program_source(prog).splitlines()[0]
+
+    # 27 rows x 128 threads x 8 B = 27 KiB: fits beside the exp table (C3) ...
+    fits = head("lactotroph", "bs23", "thresh2")
+    assert "-DCLODE_EXT_SMEM" in fits and "-DCLODE_EXT_BATCH" in fits
+    # ... but not beside exp table + polar table (stochastic stepper): registers
+    assert "-DCLODE_EXT_SMEM" not in head("lactotroph_noise", "seuler", "thresh2")
+    # the bit-exact tier stages no tables
+    assert "-DCLODE_EXT_SMEM" in head("lactotroph_noise", "seuler", "thresh2", bit_exact=True)
+    monkeypatch.setenv("CLODE_EXT_BATCH", "0")
+    assert "-DCLODE_EXT_BATCH" not in head("lactotroph", "bs23", "thresh2")
