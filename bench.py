@@ -427,7 +427,8 @@ def run_ours(args):
     base = None
     if not (args.no_cpu_baseline or is_traj or world > 1):
         base, _ = cpu_reference(args.workload, world, 1, 1)
-    sched = os.environ.get("CLODE_SCHED", "default (pilot 256 attempts, 8 sorted rounds, budget = 0.5 x dearest predicted remaining cost, >= 256)")
+    sched = os.environ.get("CLODE_SCHED", "default (pilot 64 attempts for dopri5 / 256 for bs23, 12 sorted rounds, budget = 0.35 x dearest predicted remaining cost, >= pilot)")
+    build_knobs = {k: os.environ.get(k, "default") for k in ("CLODE_BRANCHLESS", "CLODE_FAST_POLAR", "CLODE_EXT_SMEM", "CLODE_EXT_BATCH", "CLODE_IMM_HOIST")}
     line = {
         "metric": "ODE instance-steps/sec (dopri5, 1M-param sweep)", "value": value, "unit": "instance-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": dev_ms / args.steps,
@@ -439,7 +440,9 @@ def run_ours(args):
                    "kernel": info, "work_queue": bool(args.work_queue), "wall_ms_per_step": wall_ms / args.steps,
                    "scheduling": sched + ": every pass is pilot + cost-sorted rounds decided on the device from that pass alone — "
                                          "no history between passes, so the first call costs what every call costs",
-                   "first_call_ms": first_call_ms},
+                   "first_call_ms": first_call_ms,
+                   "build": dict(build_knobs, note="production double defaults: branch-free exp / rcp / div, table-log polar method, "
+                                                   "observer extents in shared memory when the features kernel spills (DESIGN.md section 3)")},
         "clocks": clocks,
         "e2e": {"value": total_steps_per_pass * args.steps / e2e_s, "unit": "instance-steps/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

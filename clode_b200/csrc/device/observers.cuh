@@ -211,8 +211,7 @@ struct Extents {
             if (I.aux[j] < c1) amin[j] = I.aux[j];
             amean[j] = mean_time(c2, I.aux[j], w);
         }
-        return;
-#endif
+#else
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             ext_max(xmax[j], I.x[j]);
@@ -227,6 +226,7 @@ struct Extents {
             ext_min(amin[j], I.aux[j]);
             amean[j] = mean_time(amean[j], I.aux[j], w);
         }
+#endif
     }
     // mean <-> integral conversion of the time-weighted means (production build, see mean_time)
     __device__ __forceinline__ void open_means(realtype span)
