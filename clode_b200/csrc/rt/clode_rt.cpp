@@ -157,6 +157,14 @@ int parse_desc(const clode_program_desc *d, ProgramSpec &s)
     s.obs_smem = d->observer_in_shared != 0 && (s.kernels & CLODE_KERNEL_FEATURES);
     s.block = d->block_size > 0 ? d->block_size : 128;
     if (s.block % 32 != 0 || s.block > 1024) return fail(CLODE_ERR_INVALID, "block_size must be a multiple of 32, <= 1024");
+    if (s.staged) {
+        // the double-buffered row tile of the staged trajectory stores (kernels.cuh) next to the math tables: within 48 KiB of
+        // static shared memory, otherwise the direct per-thread stores (the default) are used
+        size_t bytes = 2 * (size_t)(1 + 2 * s.n_var + s.n_aux) * (size_t)s.block * (s.single ? 4 : 8);
+        if (!s.single && !s.bit_exact && !s.library_exp) bytes += s.branchless ? 2048 * 8 : 128 * 16;
+        if (s.fast_polar) bytes += 256 * 24;
+        if (bytes + 1024 > 48 * 1024) s.staged = false;
+    }
     {
         // extents of the multi-variable observers in shared memory: forced by CLODE_EXT_SMEM=1, forbidden by =0, otherwise
         // decided at build time from the features kernel's spill size (clode_sim_build) — if the array fits beside the

@@ -158,3 +158,20 @@ def test_extents_go_to_shared_memory_only_when_the_array_fits(monkeypatch):
     assert "-DCLODE_EXT_SMEM" in head("lactotroph_noise", "seuler", "thresh2", bit_exact=True)
     monkeypatch.setenv("CLODE_EXT_BATCH", "0")
     assert "-DCLODE_EXT_BATCH" not in head("lactotroph", "bs23", "thresh2")
+
+
+def test_staged_trajectory_stores_fall_back_when_the_tile_does_not_fit():
+    """staged_trajectory=1 needs a double-buffered tile of (1 + 2 nVar + nAux) rows in static shared memory beside the exp
+    table: a 12-variable system does not fit in 48 KiB and is built with the direct stores instead of failing in ptxas"""
+    from clode_b200 import _rt
+
+    head = "void getRHS(const realtype t, const realtype x_[], const realtype p_[], realtype dx_[], realtype aux_[], const realtype w_[]) {\n"
+    small = _rt.Program(head + "    dx_[0] = -x_[0]; dx_[1] = exp(-x_[1]); dx_[2] = x_[0];\n}\n", "rk4", 3, 1, 0,
+                        kernels=_rt.KERNEL_TRAJECTORY, staged_trajectory=True)
+    big = _rt.Program(head + "".join(f"    dx_[{j}] = -p_[0] * x_[{j}] + exp(-x_[{(j + 1) % 12}]);\n" for j in range(12)) + "}\n", "rk4", 12, 1, 0,
+                      kernels=_rt.KERNEL_TRAJECTORY, staged_trajectory=True)
+    assert "-DCLODE_TRAJ_STAGED" in _rt.program_source(small).splitlines()[0]
+    assert "-DCLODE_TRAJ_STAGED" not in _rt.program_source(big).splitlines()[0]
+    for prog in (small, big):
+        cubin, _ = _rt.compile_program(prog)
+        assert cubin[:4] == b"\x7fELF"
