@@ -204,3 +204,22 @@ def test_extents_in_shared_memory_placement_matches_oracle(observer, batch):
     r2a = A.features((ts[1], 2 * ts[1]), got["xf"], pars, sp, op, got["dt"], got["rng"], initialize=False)
     r2b = B.features((ts[1], 2 * ts[1]), want["xf"], pars, sp, op, want["dt"], want["rng"], initialize=False)
     assert_bit_equal(r2a, r2b, cfg.tag + " continued")
+
+
+def test_extents_in_shared_memory_single_precision_and_stochastic():
+    """the same placement (with the batched loads) in single precision, and for the stochastic stepper with all-variable
+    extents: bit-identical to the oracle"""
+    defs = ("-DCLODE_EXT_SMEM", "-DCLODE_EMU_EXT_SMEM", "-DCLODE_BLOCK=128", "-DCLODE_EXT_BATCH")
+    cfg = Config("vanderpol", "dopri5", "thresh2", single=True)
+    ts, x0, pars = ensemble("vanderpol", 6)
+    sp = Solver(dt=0.1, dtmax=1.0, reltol=1e-3, max_steps=20000)
+    op = Observer(x_up_threshold=0.3, x_down_threshold=0.2)
+    A, B = EmuLib(cfg, extra_defs=defs), restate.OracleLib(cfg)
+    assert_bit_equal(run_oracle(A, "features", ts, x0, pars, sp, op), run_oracle(B, "features", ts, x0, pars, sp, op), "single precision")
+    cfg = Config("lactotroph_noise", "seuler", "basicall", math="pm")
+    ts, x0, pars = ensemble("lactotroph_noise", 5)
+    ts = (ts[0], ts[1] / 10)
+    sp = Solver(dt=0.05, dtmax=1.0, max_steps=100000)
+    A, B = EmuLib(cfg, extra_defs=defs), restate.OracleLib(cfg)
+    assert_bit_equal(run_oracle(A, "features", ts, x0, pars, sp, Observer(), seed=5), run_oracle(B, "features", ts, x0, pars, sp, Observer(), seed=5),
+                     "stochastic Euler, basicall")
